@@ -1,0 +1,472 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in this directory by running the UNMODIFIED reference.
+
+Run in the build container only (needs ``/root/reference``; it does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+What it does
+------------
+* puts ``/root/reference`` on ``sys.path`` (with empty stub modules for the plotting packages the
+  container lacks -- matplotlib, seaborn -- which the hot path never calls) and imports the
+  reference's own ``imdbn.models.{rbm,idbn,imdbn}``;
+* replaces the module-global ``torch`` seen by ``imdbn/models/rbm.py`` with a proxy that forwards
+  everything except ``rand_like`` / ``randn_like`` / ``distributions.Categorical``; those three
+  return numbers from ``oracle.philox.RandomField`` according to an explicit *draw plan*
+  (the order in which the reference draws is SURVEY.md Appendix A.7);
+* runs the reference methods on small seeded inputs and stores inputs + outputs as ``.npz``.
+
+``tests/test_oracle_golden.py`` then checks the oracle restatement against these files (CPU), and
+``tests/test_gpu_*.py`` check the CUDA path against them (GPU).
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("IMDBN_REF", "/root/reference")
+
+# ---- import the reference package first, before the repo root (which holds the drop-in
+# ---- ``imdbn`` alias package) can shadow it
+for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.cm", "matplotlib.colors",
+             "mpl_toolkits", "mpl_toolkits.mplot3d", "seaborn"):
+    if name not in sys.modules:
+        sys.modules[name] = types.ModuleType(name)
+sys.modules["mpl_toolkits.mplot3d"].Axes3D = object
+sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+sys.modules["matplotlib"].use = lambda *a, **k: None
+sys.path = [p for p in sys.path if os.path.abspath(p or ".") != REPO]
+sys.path.insert(0, REF)
+os.environ.setdefault("WANDB_MODE", "disabled")
+os.chdir(tempfile.mkdtemp(prefix="imdbn_golden_"))  # iDBN.__init__ creates logs-idbn/ in CWD
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import imdbn.models.rbm as ref_rbm_mod  # noqa: E402
+import imdbn.models.idbn as ref_idbn_mod  # noqa: E402
+import imdbn.models.imdbn as ref_imdbn_mod  # noqa: E402
+from imdbn.utils.energy_utils import rbm_free_energy  # noqa: E402
+import imdbn.utils.conditional_steps as ref_steps_mod  # noqa: E402
+from imdbn.utils.conditional_steps import _gibbs_conditional_step  # noqa: E402
+
+assert ref_rbm_mod.__file__.startswith(REF), ref_rbm_mod.__file__
+sys.path.append(REPO)
+from oracle.philox import RandomField  # noqa: E402
+from oracle import rbm_oracle as O  # noqa: E402
+
+
+# --------------------------------------------------------------------------------------------
+# RNG injection
+# --------------------------------------------------------------------------------------------
+class DrawPlan:
+    """FIFO of (kind, field, draw, group) the reference is expected to consume."""
+
+    def __init__(self):
+        self.q = []
+
+    def push(self, kind, fld, draw, group=0):
+        self.q.append((kind, fld, draw, group))
+
+    def pop(self, kind):
+        assert self.q, f"reference drew an unplanned '{kind}'"
+        k, fld, draw, group = self.q.pop(0)
+        assert k == kind, f"plan says '{k}' but the reference drew '{kind}'"
+        return fld, draw, group
+
+    def done(self):
+        assert not self.q, f"{len(self.q)} planned draws were not consumed: {self.q[:3]}"
+
+
+PLAN = DrawPlan()
+
+
+class _Categorical:
+    def __init__(self, probs=None, logits=None):
+        assert probs is not None
+        self.probs = probs
+
+    def sample(self):
+        fld, draw, group = PLAN.pop("cat")
+        u = torch.from_numpy(fld.cat_uniform(draw, self.probs.shape[0], group))
+        return O.categorical_index(self.probs, u)
+
+
+class _TorchProxy:
+    def __init__(self, real):
+        self._real = real
+        self.distributions = types.SimpleNamespace(Categorical=_Categorical)
+
+    def __getattr__(self, name):
+        return getattr(self._real, name)
+
+    def rand_like(self, x):
+        fld, draw, _ = PLAN.pop("u")
+        return torch.from_numpy(fld.uniform(draw, x.shape[0], x.shape[1])).to(x.dtype)
+
+    def randn_like(self, x):
+        fld, draw, _ = PLAN.pop("n")
+        return torch.from_numpy(fld.normal(draw, x.shape[0], x.shape[1])).to(x.dtype)
+
+
+ref_rbm_mod.torch = _TorchProxy(torch)
+ref_steps_mod.torch = ref_rbm_mod.torch   # _gibbs_conditional_step draws its own U[B,H]
+RBM = ref_rbm_mod.RBM
+
+
+# ---- draw plans (the order is the reference's; the draw numbers are our contract)
+def plan_cd(fld, k, ngroups):
+    PLAN.push("u", fld, 0)
+    for s in range(k):
+        dv, dc, dh = O.cd_draws(s)
+        PLAN.push("u", fld, dv)
+        for g in range(ngroups):
+            PLAN.push("cat", fld, dc, g)
+        PLAN.push("u", fld, dh)
+
+
+def plan_noisy(fld, n, sigma0=0.9, draw0=0):
+    PLAN.push("u", fld, draw0)
+    _, S, _ = O.noisy_mf_schedule(n, sigma0=sigma0)
+    for t in range(n):
+        if S[t] > 0:
+            PLAN.push("n", fld, draw0 + 1 + 2 * t)
+            PLAN.push("n", fld, draw0 + 2 + 2 * t)
+
+
+def plan_cond_gibbs(fld, n, sample_h, sample_v, ngroups):
+    PLAN.push("u", fld, 0)
+    for t in range(n):
+        dh, dv, dc = O.cond_gibbs_draws(t)
+        if sample_h:
+            PLAN.push("u", fld, dh)
+        if sample_v:
+            PLAN.push("u", fld, dv)
+            for g in range(ngroups):
+                PLAN.push("cat", fld, dc, g)
+
+
+def plan_clamped(fld, k, cond_init_steps, sample_h, sample_v, use_noisy_init, ngroups):
+    if use_noisy_init:
+        n = max(10, int(cond_init_steps))
+        plan_noisy(fld, n)
+        base = 1 + 2 * n
+    else:
+        plan_cond_gibbs(fld, cond_init_steps, sample_h, sample_v, ngroups)
+        base = 1 + 3 * int(cond_init_steps)
+    for s in range(k):
+        if sample_h:
+            PLAN.push("u", fld, base + 3 * s)
+        if sample_v:
+            PLAN.push("u", fld, base + 3 * s + 1)
+            for g in range(ngroups):
+                PLAN.push("cat", fld, base + 3 * s + 2, g)
+
+
+# --------------------------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------------------------
+def make_rbm(V, H, seed, groups=None, **kw):
+    hyper = dict(learning_rate=0.1, weight_decay=1e-4, momentum=0.5, dynamic_lr=True,
+                 final_momentum=0.95)
+    hyper.update(kw)
+    r = RBM(V, H, softmax_groups=groups, **hyper).to("cpu")
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        r.W.copy_(torch.randn(V, H, generator=g) / np.sqrt(V) * 3.0)   # larger than init: makes
+        r.hid_bias.copy_(torch.randn(H, generator=g) * 0.3)            # probabilities non-trivial
+        r.vis_bias.copy_(torch.randn(V, generator=g) * 0.3)
+    return r
+
+
+def params_of(r, prefix=""):
+    return {prefix + "W": r.W.detach().numpy().copy(), prefix + "hb": r.hid_bias.detach().numpy().copy(),
+            prefix + "vb": r.vis_bias.detach().numpy().copy(), prefix + "Wm": r.W_m.numpy().copy(),
+            prefix + "hbm": r.hb_m.numpy().copy(), prefix + "vbm": r.vb_m.numpy().copy()}
+
+
+def binary(B, V, seed, p=0.3):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand(B, V, generator=g) < p).float()
+
+
+def unit(B, V, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(B, V, generator=g)
+
+
+def onehot(B, K, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.nn.functional.one_hot(torch.randint(0, K, (B,), generator=g), K).float()
+
+
+def save(name, **arrs):
+    out = {}
+    for k, v in arrs.items():
+        if isinstance(v, torch.Tensor):
+            v = v.detach().cpu().numpy()
+        out[k] = np.asarray(v)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(f"wrote {name}.npz  ({sum(a.nbytes for a in out.values())/1024:.1f} KiB raw)")
+
+
+SEED = 20240611
+
+
+# --------------------------------------------------------------------------------------------
+# cases
+# --------------------------------------------------------------------------------------------
+def case_passes():
+    """forward / visible_probs / backward(return_logits) / free energy at T=1 and T=2.5."""
+    r = make_rbm(37, 19, 1, groups=[(30, 37)])
+    v = unit(9, 37, 2)
+    h = unit(9, 19, 3)
+    save("passes", **params_of(r, "in_"), groups=np.array(r.softmax_groups), v=v, h=h,
+         up_T1=r.forward(v), up_T25=r.forward(v, T=2.5),
+         down_T1=r.visible_probs(h), down_T25=r.visible_probs(h, T=2.5),
+         logits=r.backward(h, return_logits=True), backward=r.backward(h),
+         free_energy=rbm_free_energy(r, v))
+
+
+def case_train_epoch():
+    """train_epoch: plain (CD-1, CD-3, two epochs straddling the momentum switch, sparsity) and
+    with a softmax group (CD-2)."""
+    for tag, V, H, B, groups, cds, kw in [
+        ("cd_plain", 48, 24, 8, None, [1, 3, 1], {}),
+        ("cd_sparse", 33, 17, 5, None, [1, 2], dict(sparsity=True, sparsity_factor=0.1)),
+        ("cd_group", 26, 12, 7, [(20, 26)], [2, 1], {}),
+    ]:
+        r = make_rbm(V, H, 11, groups=groups, **kw)
+        data = binary(B, V, 12) if groups is None else torch.cat(
+            [unit(B, 20, 12), onehot(B, 6, 13)], dim=1)
+        out = dict(params_of(r, "in_"), data=data, seed=SEED, cds=np.array(cds),
+                   groups=np.array(groups or []).reshape(-1, 2),
+                   epochs=np.array([0, 7, 3][:len(cds)]),
+                   hyper=np.array([r.lr, r.weight_decay, r.momentum, r.final_momentum,
+                                   float(r.dynamic_lr), float(r.sparsity), r.sparsity_factor]))
+        for i, (cd, ep) in enumerate(zip(cds, out["epochs"])):
+            fld = RandomField(SEED, i)
+            plan_cd(fld, cd, len(groups or []))
+            loss = r.train_epoch(data, int(ep), 10, CD=cd)
+            PLAN.done()
+            out.update(params_of(r, f"step{i}_"))
+            out[f"step{i}_loss"] = loss
+        save(tag, **out)
+
+
+def case_noisy_mf():
+    r = make_rbm(26, 12, 21, groups=[(20, 26)])
+    B, Dz = 6, 20
+    y = onehot(B, 6, 22)
+    vk = torch.zeros(B, 26); km = torch.zeros(B, 26)
+    vk[:, Dz:] = y; km[:, Dz:] = 1.0
+    mu = unit(B, Dz, 23)
+    out = dict(params_of(r, "in_"), groups=np.array(r.softmax_groups), v_known=vk, km=km, mu=mu,
+               seed=SEED)
+    # (a) default schedule, n=12, with mu-pull
+    fld = RandomField(SEED, 0); plan_noisy(fld, 12)
+    r._mu_pull = {"mu_k": mu, "eta0": 0.15}
+    out["a"] = r.noisy_meanfield_annealed(vk, km, n_steps=12, T0=3.0, T1=1.0, sigma0=0.9,
+                                          hot_frac=0.7, sharpen_last=3, T_cold_plus=0.9)
+    PLAN.done()
+    # (b) one cold step, no noise, mu-pull fully on (the refinement call of _cross_reconstruct)
+    fld = RandomField(SEED, 1); plan_noisy(fld, 1, sigma0=0.0)
+    out["b"] = r.noisy_meanfield_annealed(out["a"], km, n_steps=1, T0=0.9, T1=0.9, sigma0=0.0,
+                                          hot_frac=0.0, sharpen_last=0, T_cold_plus=0.9)
+    PLAN.done()
+    # (c) no mu-pull, z clamped instead of y, sharpen_last=2, n=10
+    r._mu_pull = None
+    vk2 = torch.zeros(B, 26); km2 = torch.zeros(B, 26)
+    vk2[:, :Dz] = unit(B, Dz, 24); km2[:, :Dz] = 1.0
+    fld = RandomField(SEED, 2); plan_noisy(fld, 10)
+    out["c"] = r.noisy_meanfield_annealed(vk2, km2, n_steps=10, sharpen_last=2)
+    PLAN.done()
+    out["v_known2"] = vk2; out["km2"] = km2
+    save("noisy_mf", **out)
+
+
+def case_cond_gibbs():
+    r = make_rbm(26, 12, 31, groups=[(20, 26)])
+    B, Dz = 6, 20
+    vk = torch.zeros(B, 26); km = torch.zeros(B, 26)
+    vk[:, :Dz] = unit(B, Dz, 32); km[:, :Dz] = 1.0
+    out = dict(params_of(r, "in_"), groups=np.array(r.softmax_groups), v_known=vk, km=km, seed=SEED)
+    for i, (n, sh, sv) in enumerate([(7, False, False), (5, True, False), (4, True, True),
+                                     (0, False, False)]):
+        fld = RandomField(SEED, i); plan_cond_gibbs(fld, n, sh, sv, 1)
+        out[f"out{i}"] = r.conditional_gibbs(vk, km, n_steps=n, sample_h=sh, sample_v=sv)
+        PLAN.done()
+    out["cfg"] = np.array([(7, 0, 0), (5, 1, 0), (4, 1, 1), (0, 0, 0)])
+    # single conditional step (utils/conditional_steps.py:15-34)
+    v0 = unit(B, 26, 33)
+    fld = RandomField(SEED, 9)
+    PLAN.push("u", fld, 0); PLAN.push("u", fld, 1); PLAN.push("cat", fld, 2, 0)
+    vn, vp = _gibbs_conditional_step(r, v0, vk, km, sample_h=True, sample_v=True)
+    PLAN.done()
+    vn2, vp2 = _gibbs_conditional_step(r, v0, vk, km)
+    out.update(step_v0=v0, step_next=vn, step_prob=vp, step_next_mf=vn2, step_prob_mf=vp2)
+    save("cond_gibbs", **out)
+
+
+def case_clamped():
+    B, Dz = 6, 20
+    y = onehot(B, 6, 42)
+    vk = torch.zeros(B, 26); km = torch.zeros(B, 26)
+    vk[:, Dz:] = y; km[:, Dz:] = 1.0
+    cfgs = [  # (CD, cond_init_steps, sample_h, sample_v, reclamp, noisy, epoch)
+        (1, 12, False, False, True, True, 0),
+        (1, 5, False, False, False, True, 9),
+        (3, 4, True, False, True, True, 2),
+        (2, 3, True, True, True, False, 6),
+    ]
+    r = make_rbm(26, 12, 41, groups=[(20, 26)])
+    out = dict(params_of(r, "in_"), groups=np.array(r.softmax_groups), v_known=vk, km=km,
+               seed=SEED, cfg=np.array([[int(x) for x in c] for c in cfgs]),
+               hyper=np.array([r.lr, r.weight_decay, r.momentum, r.final_momentum,
+                               float(r.dynamic_lr), 0.0, r.sparsity_factor]))
+    for i, (cd, c, sh, sv, rc, noisy, ep) in enumerate(cfgs):
+        fld = RandomField(SEED, i)
+        plan_clamped(fld, cd, c, sh, sv, noisy, 1)
+        loss = r.train_epoch_clamped(vk, km, ep, 10, CD=cd, cond_init_steps=c, sample_h=sh,
+                                     sample_v=sv, reclamp_negative=rc, aux_lr_mult=0.3,
+                                     use_noisy_init=noisy)
+        PLAN.done()
+        out.update(params_of(r, f"step{i}_"))
+        out[f"step{i}_loss"] = loss
+    save("cd_clamped", **out)
+
+
+def _loader(x, y, bs):
+    ds = torch.utils.data.TensorDataset(x, y)
+    return torch.utils.data.DataLoader(ds, batch_size=bs, shuffle=False)
+
+
+PARAMS = dict(LEARNING_RATE=0.1, WEIGHT_PENALTY=1e-4, INIT_MOMENTUM=0.5, FINAL_MOMENTUM=0.95,
+              LEARNING_RATE_DYNAMIC=True, CD=1, JOINT_LEARNING_RATE=0.04, JOINT_CD=1,
+              CROSS_GIBBS_STEPS=6, JOINT_AUX_COND_STEPS=4, SPARSITY=True, SPARSITY_FACTOR=0.1)
+
+
+def _seed_idbn(model, base):
+    for i, r in enumerate(model.layers):
+        g = torch.Generator().manual_seed(base + i)
+        with torch.no_grad():
+            r.W.copy_(torch.randn(r.num_visible, r.num_hidden, generator=g) / np.sqrt(r.num_visible))
+
+
+def case_idbn():
+    """iDBN.train (2 epochs x 3 batches incl. a ragged one), represent / reconstruct / decode."""
+    N, D = 20, 40
+    x = binary(N, D, 51).view(N, 1, 5, 8)
+    y = onehot(N, 4, 52)
+    dl = _loader(x, y, 8)
+    m = ref_idbn_mod.iDBN([D, 20, 10], dict(PARAMS), dl, dl, torch.device("cpu"))
+    _seed_idbn(m, 60)
+    out = dict(x=x, y=y, seed=SEED, batch=8, epochs=2)
+    for i, r in enumerate(m.layers):
+        out.update(params_of(r, f"in_l{i}_"))
+    # stream convention: every RBM counts its own stochastic calls from 0
+    counters = [0] * len(m.layers)
+    for ep in range(2):
+        for b in range(3):
+            for li, r in enumerate(m.layers):
+                plan_cd(RandomField(SEED + li, counters[li]), 1, 0)
+                counters[li] += 1
+    m.train(2)
+    PLAN.done()
+    for i, r in enumerate(m.layers):
+        out.update(params_of(r, f"out_l{i}_"))
+    out["represent"] = m.represent(x)
+    out["represent1"] = m.represent(x, upto_layer=1)
+    out["reconstruct"] = m.reconstruct(x)
+    out["decode"] = m.decode(unit(5, 10, 53))
+    out["decode_in"] = unit(5, 10, 53)
+    save("idbn", **out)
+
+
+def case_imdbn():
+    """init_joint_bias_from_data, _cross_reconstruct (with and without a free-energy hook),
+    represent, and a short train_joint (warm-up epochs + main-phase epochs)."""
+    N, D, K = 20, 40, 4
+    x = binary(N, D, 71).view(N, 1, 5, 8)
+    y = onehot(N, K, 72)
+    dl = _loader(x, y, 8)
+    dev = torch.device("cpu")
+    m = ref_imdbn_mod.iMDBN([D, 20, 10], 8, params=dict(PARAMS), dataloader=dl, val_loader=dl,
+                            device=dev, num_labels=K)
+    _seed_idbn(m.image_idbn, 80)
+    jr = m.joint_rbm
+    g = torch.Generator().manual_seed(90)
+    with torch.no_grad():
+        jr.W.copy_(torch.randn(jr.num_visible, jr.num_hidden, generator=g) * 0.5)
+        jr.hid_bias.copy_(torch.randn(jr.num_hidden, generator=g) * 0.2)
+    out = dict(x=x, y=y, seed=SEED, batch=8, K=K)
+    for i, r in enumerate(m.image_idbn.layers):
+        out.update(params_of(r, f"in_l{i}_"))
+    out.update(params_of(jr, "in_joint_"))
+
+    m.init_joint_bias_from_data(n_batches=2)
+    out["bias_vb"] = jr.vis_bias.detach().clone()
+    out["z_class_mean"] = m.z_class_mean.clone()
+    out["z_class_count"] = m.z_class_count.clone()
+    out["represent"] = m.represent((x, y))
+
+    z = m.image_idbn.represent(x)
+    JSEED = SEED + 100
+    stream = 0
+
+    def plan_cross(stream, steps):
+        plan_cond_gibbs(RandomField(JSEED, stream), steps, False, False, 1)
+        plan_noisy(RandomField(JSEED, stream + 1), steps)
+        for c in range(4):
+            plan_noisy(RandomField(JSEED, stream + 2 + c), 1, sigma0=0.0)
+        return stream + 6
+
+    stream = plan_cross(stream, 6)
+    img, py = m._cross_reconstruct(z, y, steps=6)
+    PLAN.done()
+    out["cross_img"] = img; out["cross_py"] = py
+    # with the free-energy hook installed: best-of-K becomes live
+    RBM.free_energy = rbm_free_energy
+    stream = plan_cross(stream, 6)
+    img, py = m._cross_reconstruct(z, y, steps=6)
+    PLAN.done()
+    del RBM.free_energy
+    out["cross_img_fe"] = img; out["cross_py_fe"] = py
+
+    # ---- train_joint: 10 epochs (8 warm-up + 2 main) x 3 batches; resets the stream numbering
+    # of the joint RBM to what the drop-in does: continue counting.
+    epochs, nb = 10, 3
+    aux = PARAMS["JOINT_AUX_COND_STEPS"]
+    # init_joint_bias_from_data draws nothing
+    for ep in range(epochs):
+        for b in range(nb):
+            if ep < 8:
+                for _ in range(2):
+                    plan_clamped(RandomField(JSEED, stream), 1, aux, False, False, True, 1); stream += 1
+            else:
+                plan_cd(RandomField(JSEED, stream), PARAMS["JOINT_CD"], 1); stream += 1
+                plan_clamped(RandomField(JSEED, stream), 1, aux, False, False, True, 1); stream += 1
+                if b % 50 == 0:
+                    plan_clamped(RandomField(JSEED, stream), 1, aux, False, False, True, 1); stream += 1
+            stream = plan_cross(stream, PARAMS["CROSS_GIBBS_STEPS"])
+    m.train_joint(epochs)
+    PLAN.done()
+    out.update(params_of(jr, "out_joint_"))
+    out["train_epochs"] = epochs
+    out["final_stream"] = stream
+    save("imdbn", **out)
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(1)  # fixtures should not depend on the thread count of this machine
+    case_passes()
+    case_train_epoch()
+    case_noisy_mf()
+    case_cond_gibbs()
+    case_clamped()
+    case_idbn()
+    case_imdbn()

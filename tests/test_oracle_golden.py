@@ -1,0 +1,233 @@
+"""Pins the oracle: the restatement in ``oracle/rbm_oracle.py`` must reproduce the outputs that the
+UNMODIFIED reference produced for the same inputs and the same injected random numbers
+(fixtures written by ``tests/golden/make_golden.py``).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import rbm_oracle as O
+from oracle.philox import KAT, RandomField, philox4x32_10
+
+# The oracle repeats the reference's torch-CPU operations in the same order, so the match is
+# expected to be exact on the machine that wrote the fixtures; the tolerance only absorbs a
+# different BLAS blocking on another host.
+TOL = dict(rtol=2e-6, atol=2e-7)
+
+
+def T(a):
+    return torch.from_numpy(np.array(a))
+
+
+def state_from(g, prefix, groups=(), hyper=None):
+    kw = {}
+    if hyper is not None:
+        lr, wd, mom, fmom, dyn, sp, spf = [float(x) for x in hyper]
+        kw = dict(lr=lr, weight_decay=wd, momentum=mom, final_momentum=fmom, dynamic_lr=bool(dyn),
+                  sparsity=bool(sp), sparsity_factor=spf)
+    return O.RBMState(T(g[prefix + "W"]), T(g[prefix + "hb"]), T(g[prefix + "vb"]),
+                      T(g[prefix + "Wm"]), T(g[prefix + "hbm"]), T(g[prefix + "vbm"]),
+                      groups=[tuple(int(x) for x in r) for r in np.array(groups).reshape(-1, 2)],
+                      **kw)
+
+
+def check_params(st, g, prefix):
+    for n in ("W", "hb", "vb", "Wm", "hbm", "vbm"):
+        torch.testing.assert_close(getattr(st, n), T(g[prefix + n]), msg=lambda m: f"{prefix}{n}: {m}", **TOL)
+
+
+def test_philox_known_answers():
+    for ctr, key, out in KAT:
+        got = philox4x32_10(*ctr, *key)
+        assert tuple(int(x) for x in got) == out
+
+
+def test_uniform_range_and_row_offset():
+    f = RandomField(7, 3)
+    u = f.uniform(2, 64, 33)
+    assert u.dtype == np.float32 and u.min() >= 0.0 and u.max() < 1.0
+    # a shard starting at global row 16 sees the same numbers as rows 16.. of the full draw
+    np.testing.assert_array_equal(f.uniform(2, 8, 33, row0=16), u[16:24])
+    n = f.normal(5, 512, 512)
+    assert abs(float(n.mean())) < 0.01 and abs(float(n.std()) - 1.0) < 0.01
+
+
+def test_passes():
+    g = load_golden("passes")
+    st = state_from(g, "in_", g["groups"])
+    v, h = T(g["v"]), T(g["h"])
+    torch.testing.assert_close(O.hidden_probs(st, v), T(g["up_T1"]), **TOL)
+    torch.testing.assert_close(O.hidden_probs(st, v, 2.5), T(g["up_T25"]), **TOL)
+    torch.testing.assert_close(O.visible_probs(st, h), T(g["down_T1"]), **TOL)
+    torch.testing.assert_close(O.visible_probs(st, h, 2.5), T(g["down_T25"]), **TOL)
+    torch.testing.assert_close(O.visible_logits(st, h), T(g["logits"]), **TOL)
+    torch.testing.assert_close(O.free_energy(st, v), T(g["free_energy"]), **TOL)
+    s, e = st.groups[0]
+    assert torch.allclose(O.visible_probs(st, h)[:, s:e].sum(1), torch.ones(h.shape[0]), atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["cd_plain", "cd_sparse", "cd_group"])
+def test_train_epoch(name):
+    g = load_golden(name)
+    st = state_from(g, "in_", g["groups"], g["hyper"])
+    data = T(g["data"])
+    for i, (cd, ep) in enumerate(zip(g["cds"], g["epochs"])):
+        loss, _ = O.cd_train(st, data, int(ep), int(cd), RandomField(int(g["seed"]), i))
+        check_params(st, g, f"step{i}_")
+        torch.testing.assert_close(loss, T(g[f"step{i}_loss"]), **TOL)
+
+
+def test_noisy_meanfield():
+    g = load_golden("noisy_mf")
+    st = state_from(g, "in_", g["groups"])
+    seed = int(g["seed"])
+    vk, km, mu = T(g["v_known"]), T(g["km"]), T(g["mu"])
+    a = O.noisy_meanfield(st, vk, km, n_steps=12, mu_pull=(mu, 0.15), fld=RandomField(seed, 0))
+    torch.testing.assert_close(a, T(g["a"]), **TOL)
+    b = O.noisy_meanfield(st, T(g["a"]), km, n_steps=1, T0=0.9, T1=0.9, sigma0=0.0, hot_frac=0.0,
+                          sharpen_last=0, T_cold_plus=0.9, mu_pull=(mu, 0.15),
+                          fld=RandomField(seed, 1))
+    torch.testing.assert_close(b, T(g["b"]), **TOL)
+    c = O.noisy_meanfield(st, T(g["v_known2"]), T(g["km2"]), n_steps=10, sharpen_last=2,
+                          fld=RandomField(seed, 2))
+    torch.testing.assert_close(c, T(g["c"]), **TOL)
+
+
+def test_schedule_known_answers():
+    # SURVEY A.5
+    Ts, Ss, Es = O.noisy_mf_schedule(50, sharpen_last=3)
+    assert Ts[0] == 3.0 and abs(Ts[1] - 2.9591836) < 1e-6 and abs(Ts[46] - 1.1224489) < 1e-6
+    assert Ts[47] == Ts[48] == Ts[49] == 0.9
+    assert Ss[0] == 0.9 and abs(Ss[48] - 0.9 / 49) < 1e-9 and Ss[49] == 0.0
+    Ts, Ss, _ = O.noisy_mf_schedule(30, sharpen_last=2)
+    assert Ts[28] == Ts[29] == 0.9 and Ts[27] != 0.9 and Ss[29] == 0.0
+    Ts, Ss, Es = O.noisy_mf_schedule(1, T0=0.9, T1=0.9, sigma0=0.0, sharpen_last=0)
+    assert Ts == [0.9] and Ss == [0.0] and Es == [0.15]
+
+
+def test_conditional_gibbs():
+    g = load_golden("cond_gibbs")
+    st = state_from(g, "in_", g["groups"])
+    seed = int(g["seed"])
+    vk, km = T(g["v_known"]), T(g["km"])
+    for i, (n, sh, sv) in enumerate(g["cfg"]):
+        out = O.conditional_gibbs(st, vk, km, int(n), bool(sh), bool(sv), fld=RandomField(seed, i))
+        torch.testing.assert_close(out, T(g[f"out{i}"]), **TOL)
+    # n_steps = 0 is one un-clamped sweep from the random init (SURVEY 8c known answer)
+    f = RandomField(seed, 3)
+    v0 = vk * km + (1 - km) * torch.from_numpy(f.uniform(0, vk.shape[0], vk.shape[1]))
+    torch.testing.assert_close(O.visible_probs(st, O.hidden_probs(st, v0)), T(g["out3"]), **TOL)
+    vn, vp = O.gibbs_conditional_step(st, T(g["step_v0"]), vk, km, True, True,
+                                      fld=RandomField(seed, 9))
+    torch.testing.assert_close(vn, T(g["step_next"]), **TOL)
+    torch.testing.assert_close(vp, T(g["step_prob"]), **TOL)
+    vn, vp = O.gibbs_conditional_step(st, T(g["step_v0"]), vk, km)
+    torch.testing.assert_close(vn, T(g["step_next_mf"]), **TOL)
+
+
+def test_train_epoch_clamped():
+    g = load_golden("cd_clamped")
+    st = state_from(g, "in_", g["groups"], g["hyper"])
+    vk, km = T(g["v_known"]), T(g["km"])
+    for i, (cd, c, sh, sv, rc, noisy, ep) in enumerate(g["cfg"]):
+        loss, _ = O.cd_train_clamped(st, vk, km, int(ep), int(cd), int(c), bool(sh), bool(sv),
+                                     bool(rc), 0.3, bool(noisy),
+                                     fld=RandomField(int(g["seed"]), i))
+        check_params(st, g, f"step{i}_")
+        torch.testing.assert_close(loss, T(g[f"step{i}_loss"]), **TOL)
+
+
+IDBN_HYPER = dict(lr=0.1, weight_decay=1e-4, momentum=0.5, final_momentum=0.95, dynamic_lr=True)
+
+
+def idbn_layers(g, prefix, n=2, sparsity_last=True):
+    layers = []
+    for i in range(n):
+        st = state_from(g, f"{prefix}l{i}_")
+        for k, v in IDBN_HYPER.items():
+            setattr(st, k, v)
+        st.sparsity = sparsity_last and i == n - 1       # idbn.py:158
+        st.sparsity_factor = 0.1
+        layers.append(st)
+    return layers
+
+
+def test_idbn_train_and_chains():
+    g = load_golden("idbn")
+    layers = idbn_layers(g, "in_")
+    x = T(g["x"]).reshape(g["x"].shape[0], -1)
+    seed, bs = int(g["seed"]), int(g["batch"])
+    counters = [0, 0]
+    for ep in range(int(g["epochs"])):
+        for b0 in range(0, x.shape[0], bs):
+            flds = [RandomField(seed + li, counters[li]) for li in range(2)]
+            O.idbn_train_batch(layers, x[b0:b0 + bs], ep, 1, flds)
+            counters = [c + 1 for c in counters]
+    for i, st in enumerate(layers):
+        check_params(st, g, f"out_l{i}_")
+    torch.testing.assert_close(O.idbn_represent(layers, x), T(g["represent"]), **TOL)
+    torch.testing.assert_close(O.idbn_represent(layers, x, 1), T(g["represent1"]), **TOL)
+    torch.testing.assert_close(O.idbn_reconstruct(layers, x), T(g["reconstruct"]), **TOL)
+    torch.testing.assert_close(O.idbn_decode(layers, T(g["decode_in"])), T(g["decode"]), **TOL)
+
+
+def run_cross(layers, joint, z, y, zc, stream, seed, steps, fe):
+    out = O.cross_reconstruct(layers, joint, z, y, steps, z_class_mean=zc, use_free_energy=fe,
+                              fld_i2t=RandomField(seed, stream),
+                              fld_t2i=RandomField(seed, stream + 1),
+                              fld_refine=[RandomField(seed, stream + 2 + c) for c in range(4)])
+    return out, stream + 6
+
+
+def test_imdbn_bias_init_cross_reconstruct_and_train_joint():
+    g = load_golden("imdbn")
+    K, bs = int(g["K"]), int(g["batch"])
+    layers = idbn_layers(g, "in_")
+    joint = state_from(g, "in_joint_", [(10, 10 + K)])
+    joint.lr, joint.weight_decay, joint.momentum, joint.final_momentum, joint.dynamic_lr = \
+        0.04, 1e-4, 0.5, 0.95, True
+    x = T(g["x"]).reshape(g["x"].shape[0], -1)
+    y = T(g["y"])
+    batches = [(x[i:i + bs], y[i:i + bs]) for i in range(0, x.shape[0], bs)]
+    zs = [O.idbn_represent(layers, xb) for xb, _ in batches[:2]]
+    zc, cnt = O.joint_bias_init(joint, zs, [yb for _, yb in batches[:2]], 10, K)
+    torch.testing.assert_close(joint.vb, T(g["bias_vb"]), **TOL)
+    torch.testing.assert_close(zc, T(g["z_class_mean"]), **TOL)
+    torch.testing.assert_close(cnt, T(g["z_class_count"]), **TOL)
+    z = O.idbn_represent(layers, x)
+    torch.testing.assert_close(O.hidden_probs(joint, torch.cat([z, y], 1)), T(g["represent"]), **TOL)
+
+    seed = int(g["seed"]) + 100
+    (img, py, _, best), stream = run_cross(layers, joint, z, y, zc, 0, seed, 6, False)
+    torch.testing.assert_close(img, T(g["cross_img"]), **TOL)
+    torch.testing.assert_close(py, T(g["cross_py"]), **TOL)
+    assert int(best.max()) == 0          # no free-energy hook -> always the main chain
+    (img, py, _, best), stream = run_cross(layers, joint, z, y, zc, stream, seed, 6, True)
+    torch.testing.assert_close(img, T(g["cross_img_fe"]), **TOL)
+    torch.testing.assert_close(py, T(g["cross_py_fe"]), **TOL)
+
+    # train_joint (imdbn.py:508-639): re-runs the bias init over <=10 batches first
+    zs = [O.idbn_represent(layers, xb) for xb, _ in batches]
+    zc, _ = O.joint_bias_init(joint, zs, [yb for _, yb in batches], 10, K)
+    for ep in range(int(g["train_epochs"])):
+        for b, (xb, yb) in enumerate(batches):
+            zb = O.idbn_represent(layers, xb)
+            B = zb.shape[0]
+            vk = torch.zeros(B, 10 + K); km = torch.zeros(B, 10 + K)
+            vk[:, 10:] = yb; km[:, 10:] = 1.0
+            if ep < 8:
+                for _ in range(2):
+                    O.cd_train_clamped(joint, vk, km, ep, 1, 4, False, False, True, 0.3, True,
+                                       fld=RandomField(seed, stream)); stream += 1
+            else:
+                O.cd_train(joint, torch.cat([zb, yb], 1), ep, 1, RandomField(seed, stream)); stream += 1
+                O.cd_train_clamped(joint, vk, km, ep, 1, 4, False, False, False, 0.3, True,
+                                   fld=RandomField(seed, stream)); stream += 1
+                if b % 50 == 0:
+                    vk2 = torch.zeros(B, 10 + K); km2 = torch.zeros(B, 10 + K)
+                    vk2[:, :10] = zb; km2[:, :10] = 1.0
+                    O.cd_train_clamped(joint, vk2, km2, ep, 1, 4, False, False, False, 0.3, True,
+                                       fld=RandomField(seed, stream)); stream += 1
+            _, stream = run_cross(layers, joint, zb, yb, zc, stream, seed, 6, False)
+    assert stream == int(g["final_stream"])
+    check_params(joint, g, "out_joint_")
