@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""bench.py -- CD-k training throughput of the iDBN hot loop on B200 (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp32|tf32]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" = one minibatch of ``iDBN.train`` on [10000,1500,500], CD-1, batch 64 per GPU
+(reference idbn.py:199-204): for each layer one ``train_epoch`` and one ``forward`` with the updated
+weights.  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+import torch  # noqa: E402
+
+LAYERS = [10000, 1500, 500]
+BATCH = 64
+CD_K = 1
+PARAMS = dict(LEARNING_RATE=0.1, WEIGHT_PENALTY=1e-4, INIT_MOMENTUM=0.5, FINAL_MOMENTUM=0.95,
+              LEARNING_RATE_DYNAMIC=True, CD=CD_K, SPARSITY=False, SPARSITY_FACTOR=0.1)
+N_DISTINCT_BATCHES = 64      # 64 x 2.56 MB of inputs rotate through the steps
+METRIC = "cd_k_train_samples_per_s"
+UNIT = "samples/s"
+
+
+def step_bytes(layers, k):
+    """Algorithmic HBM bytes of one iDBN.train minibatch: per layer
+    (4 + (1+2k)) * 4 * V * H for train_epoch + 4 * V * H for the post-update forward."""
+    return sum((4 + (1 + 2 * k) + 1) * 4 * v * h for v, h in zip(layers[:-1], layers[1:]))
+
+
+def load_peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            text, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            return out
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in text.strip().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if sm:
+            out["sm_mhz"] = statistics.median(sm)
+            out["sm_max_mhz"] = max(mx)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference's CPU path for this workload: the oracle port (oracle/rbm_oracle.py restates
+    imdbn/models/{rbm,idbn}.py op for op in torch-CPU fp32), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import rbm_oracle as O
+    from oracle.philox import RandomField
+    steps, warm = args.steps, args.warmup
+    layers = [O.new_state(v, h, seed=i, lr=0.1, weight_decay=1e-4, momentum=0.5, final_momentum=0.95,
+                          dynamic_lr=True) for i, (v, h) in enumerate(zip(LAYERS[:-1], LAYERS[1:]))]
+    nb = min(N_DISTINCT_BATCHES, steps + warm)
+    data = O.synthetic_images(nb * BATCH, LAYERS[0], seed=1234)
+    t0 = None
+    for i in range(warm + steps):
+        if i == warm:
+            t0 = time.perf_counter()
+        x = data[(i % nb) * BATCH:(i % nb + 1) * BATCH]
+        O.idbn_train_batch(layers, x, 0, CD_K, [RandomField(1, 2 * i), RandomField(2, 2 * i)])
+    dt = time.perf_counter() - t0
+    val = steps * BATCH / dt
+    cores = torch.get_num_threads()
+    sample = f"{steps} minibatches of {BATCH} after {warm} warm-up, torch-CPU fp32, {cores} threads"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C2 iDBN [10000,1500,500] CD-1 batch 64 (idbn.py:199-204)"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(seconds_budget=15.0):
+    from oracle import rbm_oracle as O
+    from oracle.philox import RandomField
+    layers = [O.new_state(v, h, seed=i, lr=0.1, weight_decay=1e-4, momentum=0.5, final_momentum=0.95,
+                          dynamic_lr=True) for i, (v, h) in enumerate(zip(LAYERS[:-1], LAYERS[1:]))]
+    data = O.synthetic_images(8 * BATCH, LAYERS[0], seed=1234)
+    n, t0 = 0, None
+    while True:
+        if n == 2:
+            t0 = time.perf_counter()
+        x = data[(n % 8) * BATCH:(n % 8 + 1) * BATCH]
+        O.idbn_train_batch(layers, x, 0, CD_K, [RandomField(1, 2 * n), RandomField(2, 2 * n)])
+        n += 1
+        if t0 is not None and (time.perf_counter() - t0 > seconds_budget or n >= 66):
+            break
+    dt = time.perf_counter() - t0
+    steps = n - 2
+    cores = torch.get_num_threads()
+    return {"value": steps * BATCH / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{steps} minibatches of {BATCH} (C2 workload) after 2 warm-up, oracle port, "
+                      f"torch-CPU fp32, {cores} threads of {os.cpu_count()} cpus"}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as td
+    import multimodal_idbn_b200 as M
+    from multimodal_idbn_b200 import _lib as L
+
+    rank = M.dist.init_from_env("nccl")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    M.load_library()
+    M.set_precision(args.precision)
+    if world > 1:
+        M.dist.enable()
+
+    torch.manual_seed(0)
+    os.chdir(os.environ.get("TMPDIR", "/tmp"))       # iDBN creates logs-idbn/ in CWD (idbn.py:115)
+    model = M.iDBN(LAYERS, dict(PARAMS), None, None, dev)
+    g = torch.Generator().manual_seed(1234)
+    host = (torch.rand(N_DISTINCT_BATCHES, BATCH, LAYERS[0], generator=g) < 0.10).float().pin_memory()
+    resident = host.to(dev)
+
+    def barrier():
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        return float(t.item())
+
+    steps, warm = args.steps, args.warmup
+    # ---------------- device-resident timing: `value`
+    for i in range(warm):
+        model.train_step(resident[i % N_DISTINCT_BATCHES], 0, 1)
+    barrier()
+    sampler = ClockSampler(dev.index or 0) if rank == 0 else None
+    l0 = M.total_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        model.train_step(resident[(warm + i) % N_DISTINCT_BATCHES], 0, 1)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = M.total_launches() - l0
+    clocks = sampler.stop() if sampler else None
+    value = world * BATCH * steps / (ms * 1e-3)
+
+    # ---------------- end to end through the public API with host buffers: `e2e`
+    loss_host = torch.empty(steps + warm, len(model.layers)).pin_memory()
+
+    def e2e_loop(n, off):
+        loader = [(host[(off + i) % N_DISTINCT_BATCHES],) for i in range(n)]
+        for i, batch in enumerate(M.prefetch_to_device(loader, dev)):
+            losses = model.train_step(batch[0], 0, 1)
+            loss_host[off + i].copy_(torch.stack(losses), non_blocking=True)   # D2H read of the result
+
+    e2e_loop(warm, 0)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_loop(steps, warm)
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    e2e_val = world * BATCH * steps / (e2e_ms * 1e-3)
+    assert torch.isfinite(loss_host[warm:]).all()
+
+    # ---------------- roofline of the dominant kernel (layer-0 statistics + update), CUDA events
+    ctx, _ = L.context_for(model.layers[0].W)
+    ctx.profile(True)
+    n_prof = min(steps, 20)
+    for i in range(n_prof):
+        model.train_step(resident[i % N_DISTINCT_BATCHES], 0, 1)
+    torch.cuda.synchronize()
+    V0, H0 = LAYERS[0], LAYERS[1]
+    kern = {}
+    for name, kind in (("up", L.KERNEL_UP), ("down", L.KERNEL_DOWN), ("stats_update", L.KERNEL_STATS)):
+        tot, cnt = ctx.profile_read(kind, V0, H0)
+        kern[name] = {"ms_avg": tot / max(1, cnt), "launches": cnt}
+    ctx.profile(False)
+    peak, peak_src = load_peaks()
+    upd_bytes = 4 * 4 * V0 * H0                      # read W, W_m; write W, W_m
+    pass_bytes = 4 * V0 * H0
+    ach = upd_bytes / (kern["stats_update"]["ms_avg"] * 1e-3) / 1e9 if kern["stats_update"]["ms_avg"] else None
+    sb = step_bytes(LAYERS, CD_K)
+    step_gbs = sb / (ms / steps * 1e-3) / 1e9
+
+    if rank != 0:
+        return
+    cpu = cpu_baseline() if world == 1 and not args.no_cpu_baseline else None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+        "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if args.precision == "fp32" else "tf32", "data": "synthetic",
+        "config": {"workload": "C2 iDBN [10000,1500,500] CD-1 batch 64 per GPU (idbn.py:199-204)",
+                   "global_batch": BATCH * world,
+                   "parallelism": f"dp{world} (batch-sharded, dS all-reduce)" if world > 1 else "single GPU",
+                   "precision_mode": args.precision,
+                   "l2": "state (W, W_m of both layers: 252 MB) + 164 MB of rotating inputs exceed the "
+                         "126 MB L2; no explicit flush"},
+        "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": e2e_ms / steps,
+                "h2d_bytes_per_step": BATCH * LAYERS[0] * 4, "d2h_bytes_per_step": 4 * len(model.layers)},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "layer-0 CD statistics + momentum/weight-decay update",
+                     "achieved": ach, "peak": peak, "unit": "GB/s",
+                     "frac": (ach / peak) if ach else None, "traffic": None,
+                     "algorithmic_bytes_per_launch": upd_bytes, "peak_source": peak_src,
+                     "avg_launch_ms": kern["stats_update"]["ms_avg"]},
+        "kernels": {k: dict(v, gbs=(pass_bytes if k != "stats_update" else upd_bytes) /
+                            (v["ms_avg"] * 1e-3) / 1e9 if v["ms_avg"] else None) for k, v in kern.items()},
+        "roofline_step": {"algorithmic_bytes": sb, "achieved_gbs": step_gbs, "frac": step_gbs / peak},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        if args.steps > 64:
+            args.steps = 64            # bounded sample: ~0.2 s per CPU step
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

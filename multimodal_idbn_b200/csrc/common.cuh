@@ -1,0 +1,154 @@
+// Context, workspace arena and launch bookkeeping shared by the kernels of libimdbn_b200.so.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+
+#include "../../include/imdbn_b200.h"
+#include "philox.cuh"
+
+namespace imdbn {
+
+constexpr int kNumSMsFallback = 148;  // B200
+
+struct Arena {
+    char* base = nullptr;
+    size_t cap = 0;
+    size_t off = 0;
+};
+
+}  // namespace imdbn
+
+namespace imdbn {
+struct ProfRec { int kind, V, H; cudaEvent_t a, b; };
+}
+
+struct imdbn_ctx {
+    bool profile = false;
+    std::vector<imdbn::ProfRec> prof;
+    int device = 0;
+    int num_sms = imdbn::kNumSMsFallback;
+    int precision = IMDBN_PREC_FP32;
+    int64_t launches = 0;
+    std::string err;
+    imdbn::Arena arena;
+    // transposed-weight cache for the chain kernels is rebuilt on every call (W changes between
+    // updates); it lives in the arena like everything else.
+    void* tc = nullptr;  // tensor-core path state (tc_gemm.cu), opaque here
+};
+
+namespace imdbn {
+
+inline int fail(imdbn_ctx* ctx, int code, const char* what) {
+    if (ctx) {
+        ctx->err = what;
+        if (code > 0) {
+            ctx->err += ": ";
+            ctx->err += cudaGetErrorString((cudaError_t)code);
+        }
+    }
+    return code;
+}
+
+#define IMDBN_CUDA(ctx, expr)                                             \
+    do {                                                                  \
+        cudaError_t _e = (expr);                                          \
+        if (_e != cudaSuccess) return imdbn::fail((ctx), (int)_e, #expr); \
+    } while (0)
+
+#define IMDBN_CHECK_LAUNCH(ctx, name)                                         \
+    do {                                                                      \
+        (ctx)->launches++;                                                    \
+        cudaError_t _e = cudaGetLastError();                                  \
+        if (_e != cudaSuccess) return imdbn::fail((ctx), (int)_e, "launch " name); \
+    } while (0)
+
+#define IMDBN_ARG(ctx, cond)                                             \
+    do {                                                                 \
+        if (!(cond)) return imdbn::fail((ctx), -1, "invalid argument: " #cond); \
+    } while (0)
+
+// RAII bracket of one kernel launch with CUDA events on the launching stream (profile mode only).
+struct ProfScope {
+    imdbn_ctx* ctx; cudaStream_t st; ProfRec rec; bool on;
+    ProfScope(imdbn_ctx* c, int kind, int V, int H, cudaStream_t s) : ctx(c), st(s), on(c->profile) {
+        if (!on) return;
+        rec.kind = kind; rec.V = V; rec.H = H;
+        cudaEventCreate(&rec.a); cudaEventCreate(&rec.b);
+        cudaEventRecord(rec.a, st);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(rec.b, st);
+        ctx->prof.push_back(rec);
+    }
+};
+
+// Reserve `total` bytes for the current API call.  Growing synchronises the stream once (sizes
+// settle after the first calls); buffers are only valid until the next API call on this context.
+inline int arena_begin(imdbn_ctx* ctx, size_t total, cudaStream_t st) {
+    total += 4096;
+    if (total > ctx->arena.cap) {
+        IMDBN_CUDA(ctx, cudaStreamSynchronize(st));
+        if (ctx->arena.base) IMDBN_CUDA(ctx, cudaFree(ctx->arena.base));
+        ctx->arena.base = nullptr;
+        ctx->arena.cap = 0;
+        size_t cap = total + total / 4;
+        IMDBN_CUDA(ctx, cudaMalloc((void**)&ctx->arena.base, cap));
+        ctx->arena.cap = cap;
+    }
+    ctx->arena.off = 0;
+    return 0;
+}
+
+template <typename T>
+inline T* arena_take(imdbn_ctx* ctx, size_t n) {
+    size_t bytes = (n * sizeof(T) + 255) & ~size_t(255);
+    T* p = reinterpret_cast<T*>(ctx->arena.base + ctx->arena.off);
+    ctx->arena.off += bytes;
+    return p;
+}
+
+inline size_t pad256(size_t n_floats) { return (n_floats * 4 + 255) & ~size_t(255); }
+
+inline RngKey make_key(const imdbn_rng* r) {
+    RngKey k;
+    k.k0 = (uint32_t)(r->seed & 0xFFFFFFFFull);
+    k.k1 = (uint32_t)(r->seed >> 32);
+    k.stream = r->stream;
+    k.row0 = r->row0;
+    return k;
+}
+
+struct Groups {
+    int n;
+    int s[IMDBN_MAX_GROUPS];
+    int e[IMDBN_MAX_GROUPS];
+};
+
+inline Groups make_groups(const imdbn_rbm* r) {
+    Groups g;
+    g.n = r->ngroups;
+    for (int i = 0; i < IMDBN_MAX_GROUPS; ++i) {
+        g.s[i] = i < r->ngroups ? r->group_start[i] : 0;
+        g.e[i] = i < r->ngroups ? r->group_end[i] : 0;
+    }
+    return g;
+}
+
+// exact (never FMA-contracted) forms of the reference's element-wise expressions
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+
+// rbm.py:19-21 hand-rolled sigmoid and torch.sigmoid agree to 1 ulp; one device form for both.
+__device__ __forceinline__ float sigmoidf_ref(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// v = a*(1-km) + known*km  (rbm.py:291,365,397) without contraction
+__device__ __forceinline__ float clampmix(float a, float known, float km) {
+    return add_rn(mul_rn(a, 1.0f - km), mul_rn(known, km));
+}
+
+}  // namespace imdbn

@@ -1,0 +1,627 @@
+// libimdbn_b200.so -- C ABI (include/imdbn_b200.h) over the sm_100a kernels.
+// Host-side sequencing of the reference's RBM methods (imdbn/models/rbm.py); every function only
+// enqueues kernels on the caller's stream.
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "gemm_ffma.cuh"
+#include "rbm_kernels.cuh"
+#include "chain_kernel.cuh"
+#include "tc_gemm.cuh"
+
+using namespace imdbn;
+
+namespace {
+
+void prof_clear(imdbn_ctx* ctx) {
+    for (auto& r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    ctx->prof.clear();
+}
+
+inline int ew_blocks(size_t n, int num_sms) {
+    size_t b = (n + 255) / 256;
+    size_t cap = (size_t)num_sms * 8;
+    return (int)std::max<size_t>(1, std::min(b, cap));
+}
+
+struct PassPlan {
+    int splits;
+    int kps;
+    size_t part_floats;
+};
+
+PassPlan plan_pass(const imdbn_ctx* ctx, int M, int N, int K) {
+    PassPlan p;
+    p.splits = choose_splits(M, N, K, ctx->num_sms);
+    int kps = (K + p.splits - 1) / p.splits;
+    kps = (kps + GBK - 1) / GBK * GBK;
+    p.kps = kps;
+    p.splits = (K + kps - 1) / kps;
+    p.part_floats = (size_t)p.splits * M * N;
+    return p;
+}
+
+// part[s][B][H] = v[B,V] . W[V,H]   (K split over blockIdx.z)
+int gemm_up(imdbn_ctx* ctx, const imdbn_rbm* r, const float* v, int B, const PassPlan& pl,
+            float* part, cudaStream_t st) {
+    ProfScope prof(ctx, IMDBN_KERNEL_UP, r->V, r->H, st);
+    if (ctx->precision == IMDBN_PREC_TF32 && tc_up_supported(ctx, r, B))
+        return tc_gemm_up(ctx, r, v, B, part, st);
+    GemmArgs g{};
+    g.A = v; g.sAm = r->V; g.sAk = 1;
+    g.B = r->W; g.sBk = r->H; g.sBn = 1;
+    g.M = B; g.N = r->H; g.K = r->V;
+    g.k_per_split = pl.kps; g.C = part;
+    dim3 grid((g.N + GBN - 1) / GBN, (g.M + GBM - 1) / GBM, pl.splits);
+    k_gemm_ffma<true, true, EPI_STORE><<<grid, GTHREADS, 0, st>>>(g);
+    IMDBN_CHECK_LAUNCH(ctx, "k_gemm_ffma(up)");
+    return 0;
+}
+
+// part[s][B][V] = h[B,H] . W[V,H]^T
+int gemm_down(imdbn_ctx* ctx, const imdbn_rbm* r, const float* h, int B, const PassPlan& pl,
+              float* part, cudaStream_t st) {
+    ProfScope prof(ctx, IMDBN_KERNEL_DOWN, r->V, r->H, st);
+    if (ctx->precision == IMDBN_PREC_TF32 && tc_down_supported(ctx, r, B))
+        return tc_gemm_down(ctx, r, h, B, part, st);
+    GemmArgs g{};
+    g.A = h; g.sAm = r->H; g.sAk = 1;
+    g.B = r->W; g.sBk = 1; g.sBn = r->H;
+    g.M = B; g.N = r->V; g.K = r->H;
+    g.k_per_split = pl.kps; g.C = part;
+    dim3 grid((g.N + GBN - 1) / GBN, (g.M + GBM - 1) / GBM, pl.splits);
+    k_gemm_ffma<true, false, EPI_STORE><<<grid, GTHREADS, 0, st>>>(g);
+    IMDBN_CHECK_LAUNCH(ctx, "k_gemm_ffma(down)");
+    return 0;
+}
+
+// dS[V,H] = vp^T hp - vn^T hn, either stored (dS_out) or consumed by the fused update.
+int gemm_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* vp, const float* hp,
+               const float* vn, const float* hn, int B, float* dS_out, const imdbn_update* upd,
+               cudaStream_t st) {
+    ProfScope prof(ctx, IMDBN_KERNEL_STATS, r->V, r->H, st);
+    if (ctx->precision == IMDBN_PREC_TF32 && tc_stats_supported(ctx, r, B))
+        return tc_gemm_stats(ctx, r, vp, hp, vn, hn, B, dS_out, upd, st);
+    GemmArgs g{};
+    g.A = vp; g.sAm = 1; g.sAk = r->V;
+    g.B = hp; g.sBk = r->H; g.sBn = 1;
+    g.A2 = vn; g.B2 = hn; g.K2 = B;
+    g.M = r->V; g.N = r->H; g.K = B;
+    g.k_per_split = B;
+    dim3 grid((g.N + GBN - 1) / GBN, (g.M + GBM - 1) / GBM, 1);
+    if (dS_out) {
+        g.C = dS_out;
+        k_gemm_ffma<false, true, EPI_STORE><<<grid, GTHREADS, 0, st>>>(g);
+    } else {
+        g.W = r->W; g.Wm = r->Wm;
+        g.lr = upd->lr; g.mom = upd->momentum; g.wd = upd->weight_decay;
+        g.bsz = (float)upd->batch_global;
+        k_gemm_ffma<false, true, EPI_UPDATE><<<grid, GTHREADS, 0, st>>>(g);
+    }
+    IMDBN_CHECK_LAUNCH(ctx, "k_gemm_ffma(stats)");
+    return 0;
+}
+
+int up_pass(imdbn_ctx* ctx, const imdbn_rbm* r, const float* v, int B, float T, float* p_out,
+            float* s_out, const RngKey& key, uint32_t draw_u, const PassPlan& pl, float* part,
+            cudaStream_t st) {
+    int rc = gemm_up(ctx, r, v, B, pl, part, st);
+    if (rc) return rc;
+    k_finish_up<<<ew_blocks((size_t)B * r->H, ctx->num_sms), 256, 0, st>>>(
+        part, pl.splits, B, r->H, r->hb, fmaxf(1e-6f, T), p_out, s_out, key, draw_u);
+    IMDBN_CHECK_LAUNCH(ctx, "k_finish_up");
+    return 0;
+}
+
+int down_pass(imdbn_ctx* ctx, const imdbn_rbm* r, const float* h, int B, float T, float* p_out,
+              float* logits_out, float* s_out, float* logits_tmp, const RngKey& key,
+              uint32_t draw_u, uint32_t draw_cat, const PassPlan& pl, float* part,
+              cudaStream_t st) {
+    int rc = gemm_down(ctx, r, h, B, pl, part, st);
+    if (rc) return rc;
+    const Groups gr = make_groups(r);
+    float* lg = logits_out ? logits_out : (gr.n ? logits_tmp : nullptr);
+    k_finish_down<<<ew_blocks((size_t)B * r->V, ctx->num_sms), 256, 0, st>>>(
+        part, pl.splits, B, r->V, r->vb, fmaxf(1e-6f, T), p_out, lg, s_out, key, draw_u);
+    IMDBN_CHECK_LAUNCH(ctx, "k_finish_down");
+    if (gr.n && (p_out || s_out)) {
+        // the groups need a probability buffer even when the caller only wants samples
+        float* pbuf = p_out ? p_out : logits_tmp + (size_t)B * r->V;
+        const int warps = B * gr.n;
+        k_groups<<<(warps * 32 + 127) / 128, 128, 0, st>>>(lg, pbuf, s_out, B, r->V, gr, key, draw_cat);
+        IMDBN_CHECK_LAUNCH(ctx, "k_groups");
+    }
+    return 0;
+}
+
+int check_rbm(imdbn_ctx* ctx, const imdbn_rbm* r, bool need_momenta) {
+    IMDBN_ARG(ctx, r != nullptr);
+    IMDBN_ARG(ctx, r->W && r->hb && r->vb);
+    IMDBN_ARG(ctx, r->V > 0 && r->H > 0);
+    IMDBN_ARG(ctx, r->ngroups >= 0 && r->ngroups <= IMDBN_MAX_GROUPS);
+    for (int g = 0; g < r->ngroups; ++g)
+        IMDBN_ARG(ctx, r->group_start[g] >= 0 && r->group_start[g] < r->group_end[g] &&
+                           r->group_end[g] <= r->V);
+    if (need_momenta) IMDBN_ARG(ctx, r->Wm && r->hbm && r->vbm);
+    return 0;
+}
+
+int finish_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* hp, const float* hn,
+                 const float* vp, const float* vn, const float* ea, const float* eb, int B,
+                 float* st_small, float* sq_part, cudaStream_t st) {
+    const int cols = std::max(r->V, r->H);
+    const int nb = (cols + 255) / 256;
+    k_colstats<<<nb, 256, 0, st>>>(hp, hn, vp, vn, ea, eb, B, r->V, r->H, st_small, sq_part);
+    IMDBN_CHECK_LAUNCH(ctx, "k_colstats");
+    k_sum_partials<<<1, 256, 0, st>>>(sq_part, nb, st_small + 2 * r->H + r->V);
+    IMDBN_CHECK_LAUNCH(ctx, "k_sum_partials");
+    return 0;
+}
+
+int bias_update(imdbn_ctx* ctx, const imdbn_rbm* r, const float* st_small, const imdbn_update* u,
+                float n_loss, float* loss_out, cudaStream_t st) {
+    const int cols = std::max(r->V, r->H);
+    k_bias_update<<<(cols + 255) / 256, 256, 0, st>>>(st_small, r->V, r->H, r->hb, r->hbm, r->vb,
+                                                      r->vbm, u->lr, u->momentum,
+                                                      (float)u->batch_global, u->sparsity,
+                                                      u->sparsity_target, n_loss, loss_out);
+    IMDBN_CHECK_LAUNCH(ctx, "k_bias_update");
+    return 0;
+}
+
+// ---- chain launcher -------------------------------------------------------------------------
+template <int R>
+int launch_chain_r(imdbn_ctx* ctx, const ChainArgs& a, size_t smem, cudaStream_t st) {
+    ProfScope prof(ctx, IMDBN_KERNEL_CHAIN, a.V, a.H, st);
+    IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_chain<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem));
+    k_chain<R><<<(a.B + R - 1) / R, CHAIN_THREADS, smem, st>>>(a);
+    IMDBN_CHECK_LAUNCH(ctx, "k_chain");
+    return 0;
+}
+
+size_t chain_ws_floats(const imdbn_rbm* r, int n_steps) {
+    return (size_t)r->V * r->H + 3 * (size_t)std::max(1, n_steps) + 256;
+}
+
+// Wt / tables must come from the arena of the current call.
+int run_chain(imdbn_ctx* ctx, const imdbn_rbm* r, const imdbn_chain* ch, int B, float* v_out,
+              float* vprob_out, const RngKey& key, float* Wt, float* tables, cudaStream_t st) {
+    IMDBN_ARG(ctx, ch->n_steps >= 0 && ch->n_steps <= CHAIN_MAX_STEPS);
+    IMDBN_ARG(ctx, ch->v_known && ch->known_mask);
+    ChainArgs a{};
+    a.W = r->W; a.Wt = Wt; a.hb = r->hb; a.vb = r->vb;
+    a.V = r->V; a.H = r->H; a.B = B;
+    a.gr = make_groups(r);
+    a.kind = ch->kind; a.n_steps = ch->n_steps;
+    a.v_known = ch->v_known; a.km = ch->known_mask; a.v_init = ch->v_init;
+    a.mu = ch->mu; a.Dz = ch->Dz;
+    a.sample_h = ch->sample_h; a.sample_v = ch->sample_v; a.final_free = ch->final_free_sweep;
+    a.draw0 = ch->draw0;
+    a.v_out = v_out; a.vprob_out = vprob_out;
+    a.key = key;
+    a.Vp = (r->V + 3) & ~3; a.Hp = (r->H + 3) & ~3;
+    const int n = ch->n_steps;
+    if (ch->kind == IMDBN_CHAIN_NOISY_MF) {
+        IMDBN_ARG(ctx, n == 0 || (ch->T && ch->sigma));
+        std::vector<float> host(3 * (size_t)std::max(1, n), 0.0f);
+        for (int t = 0; t < n; ++t) {
+            host[t] = fmaxf(1e-6f, ch->T[t]);
+            host[n + t] = ch->sigma[t];
+            host[2 * n + t] = ch->eta ? ch->eta[t] : 0.0f;
+        }
+        IMDBN_CUDA(ctx, cudaMemcpyAsync(tables, host.data(), host.size() * sizeof(float),
+                                        cudaMemcpyHostToDevice, st));
+        a.T = tables; a.sigma = tables + n; a.eta = tables + 2 * n;
+    }
+    dim3 tb(32, 8), tg((r->H + 31) / 32, (r->V + 31) / 32);
+    k_transpose<<<tg, tb, 0, st>>>(r->W, r->V, r->H, Wt);
+    IMDBN_CHECK_LAUNCH(ctx, "k_transpose");
+
+    const size_t per_row = (size_t)(2 * a.Vp + a.Hp) * sizeof(float);
+    int R = 16;
+    while (R > 1 && ((B + R - 1) / R < 2 * ctx->num_sms || per_row * R > 100 * 1024)) R >>= 1;
+    const size_t smem = per_row * R;
+    if (smem > 227 * 1024) return fail(ctx, -2, "chain state does not fit in shared memory");
+    switch (R) {
+        case 16: return launch_chain_r<16>(ctx, a, smem, st);
+        case 8:  return launch_chain_r<8>(ctx, a, smem, st);
+        case 4:  return launch_chain_r<4>(ctx, a, smem, st);
+        case 2:  return launch_chain_r<2>(ctx, a, smem, st);
+        default: return launch_chain_r<1>(ctx, a, smem, st);
+    }
+}
+
+// shared body of cd_train / cd_stats
+int cd_core(imdbn_ctx* ctx, const imdbn_rbm* r, const float* data, int B, int k,
+            const imdbn_update* upd, const imdbn_rng* rng, float* loss_out, float* stats_out,
+            cudaStream_t st) {
+    int rc = check_rbm(ctx, r, stats_out == nullptr);
+    if (rc) return rc;
+    IMDBN_ARG(ctx, data && B > 0 && k >= 1 && rng);
+    const int V = r->V, H = r->H;
+    const PassPlan pu = plan_pass(ctx, B, H, V), pd = plan_pass(ctx, B, V, H);
+    const size_t nBH = (size_t)B * H, nBV = (size_t)B * V;
+    const int nb_sq = (std::max(V, H) + 255) / 256;
+    size_t bytes = pad256(std::max(pu.part_floats, pd.part_floats)) + 3 * pad256(nBH) +
+                   4 * pad256(nBV) + pad256(2 * H + V + 1) + pad256(nb_sq) +
+                   tc_ws_bytes(ctx, r, B);
+    rc = arena_begin(ctx, bytes, st);
+    if (rc) return rc;
+    float* part = arena_take<float>(ctx, std::max(pu.part_floats, pd.part_floats));
+    float* pos_h = arena_take<float>(ctx, nBH);
+    float* h_s = arena_take<float>(ctx, nBH);
+    float* h_prob = arena_take<float>(ctx, nBH);
+    float* v_prob = arena_take<float>(ctx, nBV);
+    float* v_s = arena_take<float>(ctx, nBV);
+    float* lg_tmp = arena_take<float>(ctx, 2 * nBV);
+    float* st_small = stats_out ? stats_out + (size_t)V * H : arena_take<float>(ctx, 2 * H + V + 1);
+    float* sq_part = arena_take<float>(ctx, nb_sq);
+    const RngKey key = make_key(rng);
+
+    rc = up_pass(ctx, r, data, B, 1.0f, pos_h, h_s, key, 0, pu, part, st);          // rbm.py:199,203
+    if (rc) return rc;
+    for (int s = 0; s < k; ++s) {
+        rc = down_pass(ctx, r, h_s, B, 1.0f, v_prob, nullptr, v_s, lg_tmp, key, 1 + 3 * s,
+                       2 + 3 * s, pd, part, st);                                        // :205-206
+        if (rc) return rc;
+        rc = up_pass(ctx, r, v_s, B, 1.0f, h_prob, (s + 1 < k) ? h_s : nullptr, key, 3 + 3 * s, pu,
+                     part, st);                                                         // :207-208
+        if (rc) return rc;
+    }
+    // bias / loss statistics must read W-independent buffers only, so order vs. the fused weight
+    // update does not matter; keep the reference's order (weights first).
+    rc = gemm_stats(ctx, r, data, pos_h, v_s, h_prob, B, stats_out, upd, st);           // :200,209,212
+    if (rc) return rc;
+    rc = finish_stats(ctx, r, pos_h, h_prob, data, v_s, data, v_prob, B, st_small, sq_part, st);
+    if (rc) return rc;
+    if (!stats_out)
+        rc = bias_update(ctx, r, st_small, upd, (float)upd->batch_global * V, loss_out, st);
+    return rc;
+}
+
+int clamped_core(imdbn_ctx* ctx, const imdbn_rbm* r, const float* v_known, const float* km, int B,
+                 const imdbn_clamped_cfg* cfg, const imdbn_update* upd, const imdbn_rng* rng,
+                 float* loss_out, float* stats_out, cudaStream_t st) {
+    int rc = check_rbm(ctx, r, stats_out == nullptr);
+    if (rc) return rc;
+    IMDBN_ARG(ctx, v_known && km && B > 0 && cfg && rng && cfg->k >= 0);
+    const int V = r->V, H = r->H;
+    const int n = cfg->use_noisy_init ? std::max(10, cfg->cond_init_steps) : cfg->cond_init_steps;
+    IMDBN_ARG(ctx, n >= 0 && n <= CHAIN_MAX_STEPS);
+    const PassPlan pu = plan_pass(ctx, B, H, V), pd = plan_pass(ctx, B, V, H);
+    const size_t nBH = (size_t)B * H, nBV = (size_t)B * V;
+    const int nb_sq = (std::max(V, H) + 255) / 256;
+    size_t bytes = pad256(std::max(pu.part_floats, pd.part_floats)) + 3 * pad256(nBH) +
+                   5 * pad256(nBV) + pad256(2 * H + V + 1) + pad256(nb_sq) +
+                   pad256(chain_ws_floats(r, n)) + 1024 + tc_ws_bytes(ctx, r, B);
+    rc = arena_begin(ctx, bytes, st);
+    if (rc) return rc;
+    float* part = arena_take<float>(ctx, std::max(pu.part_floats, pd.part_floats));
+    float* h_plus = arena_take<float>(ctx, nBH);
+    float* h_cur = arena_take<float>(ctx, nBH);
+    float* h_neg = arena_take<float>(ctx, nBH);
+    float* v_plus = arena_take<float>(ctx, nBV);
+    float* v_prob = arena_take<float>(ctx, nBV);
+    float* v_neg = arena_take<float>(ctx, nBV);
+    float* lg_tmp = arena_take<float>(ctx, 2 * nBV);
+    float* st_small = stats_out ? stats_out + (size_t)V * H : arena_take<float>(ctx, 2 * H + V + 1);
+    float* sq_part = arena_take<float>(ctx, nb_sq);
+    float* Wt = arena_take<float>(ctx, (size_t)V * H);
+    float* tables = arena_take<float>(ctx, 3 * (size_t)std::max(1, n));
+    const RngKey key = make_key(rng);
+
+    // positive phase: conditional inference (rbm.py:443-453)
+    imdbn_chain ch{};
+    std::vector<float> T, S, E;
+    ch.v_known = v_known; ch.known_mask = km; ch.n_steps = n; ch.draw0 = 0;
+    uint32_t base;
+    if (cfg->use_noisy_init) {
+        // T0=3, T1=1, sigma0=.9, sharpen_last=2, T_cold_plus=.9 (rbm.py:444-448, schedule :229-234,338-341)
+        T.resize(n); S.resize(n); E.assign(n, 0.0f);
+        for (int t = 0; t < n; ++t) {
+            double Tt = 1.0;
+            if (n > 1) {
+                double al = std::min(std::max((double)t / (n - 1), 0.0), 1.0);
+                Tt = 3.0 + (1.0 - 3.0) * al;
+            }
+            if (n - t <= 2) Tt = 0.9;
+            T[t] = (float)std::max(1e-6, Tt);
+            S[t] = (float)(0.9 * std::max(0.0, 1.0 - (double)t / std::max(1, n - 1)));
+        }
+        ch.kind = IMDBN_CHAIN_NOISY_MF; ch.T = T.data(); ch.sigma = S.data(); ch.eta = E.data();
+        base = 1 + 2 * n;
+    } else {
+        ch.kind = IMDBN_CHAIN_COND_GIBBS; ch.sample_h = cfg->sample_h; ch.sample_v = cfg->sample_v;
+        ch.final_free_sweep = 1;
+        base = 1 + 3 * n;
+    }
+    rc = run_chain(ctx, r, &ch, B, v_plus, nullptr, key, Wt, tables, st);
+    if (rc) return rc;
+    rc = up_pass(ctx, r, v_plus, B, 1.0f, h_plus, nullptr, key, 0, pu, part, st);       // :455
+    if (rc) return rc;
+    const float* vcur = v_plus;
+    for (int s = 0; s < cfg->k; ++s) {                                                  // :460-469
+        rc = up_pass(ctx, r, vcur, B, 1.0f, cfg->sample_h ? nullptr : h_cur,
+                     cfg->sample_h ? h_cur : nullptr, key, base + 3 * s, pu, part, st);
+        if (rc) return rc;
+        rc = down_pass(ctx, r, h_cur, B, 1.0f, v_prob, nullptr, nullptr, lg_tmp, key, 0, 0, pd,
+                       part, st);
+        if (rc) return rc;
+        const float* vn = v_prob;
+        if (cfg->reclamp_negative) {
+            k_clampmix<<<ew_blocks(nBV, ctx->num_sms), 256, 0, st>>>(v_prob, v_known, km, nBV, v_neg);
+            IMDBN_CHECK_LAUNCH(ctx, "k_clampmix");
+            vn = v_neg;
+        }
+        if (cfg->sample_v) {
+            // sample_visible(v_neg) (rbm.py:469): Bernoulli everywhere, categorical per group
+            float* dst = (vn == v_neg) ? v_prob : v_neg;
+            IMDBN_CUDA(ctx, cudaMemcpyAsync(lg_tmp, vn, nBV * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            k_bernoulli<<<ew_blocks(nBV, ctx->num_sms), 256, 0, st>>>(vn, B, V, dst, key, base + 3 * s + 1);
+            IMDBN_CHECK_LAUNCH(ctx, "k_bernoulli");
+            const Groups gr = make_groups(r);
+            if (gr.n) {
+                k_groups<<<(B * gr.n * 32 + 127) / 128, 128, 0, st>>>(nullptr, lg_tmp, dst, B, V, gr, key,
+                                                                      base + 3 * s + 2);
+                IMDBN_CHECK_LAUNCH(ctx, "k_groups");
+            }
+            vn = dst;
+        }
+        if (vn != v_neg) {
+            IMDBN_CUDA(ctx, cudaMemcpyAsync(v_neg, vn, nBV * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        }
+        vcur = v_neg;
+    }
+    if (cfg->k == 0)
+        IMDBN_CUDA(ctx, cudaMemcpyAsync(v_neg, v_plus, nBV * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    rc = up_pass(ctx, r, v_neg, B, 1.0f, h_neg, nullptr, key, 0, pu, part, st);         // :471
+    if (rc) return rc;
+    rc = gemm_stats(ctx, r, v_plus, h_plus, v_neg, h_neg, B, stats_out, upd, st);       // :456,472,476
+    if (rc) return rc;
+    rc = finish_stats(ctx, r, h_plus, h_neg, v_plus, v_neg, v_plus, v_neg, B, st_small, sq_part, st);
+    if (rc) return rc;
+    if (!stats_out) {
+        imdbn_update u = *upd;
+        u.sparsity = 0;                                                                 // :478-481
+        rc = bias_update(ctx, r, st_small, &u, (float)upd->batch_global * V, loss_out, st);
+    }
+    return rc;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int imdbn_abi_version(void) { return IMDBN_ABI_VERSION; }
+
+int imdbn_ctx_create(imdbn_ctx** out, int device) {
+    if (!out) return -1;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess) return (int)e;
+    if (device < 0 || device >= ndev) return -1;
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return (int)e;
+    imdbn_ctx* c = new imdbn_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
+        c->num_sms = prop.multiProcessorCount;
+        if (prop.major < 10) {
+            delete c;
+            return -3;  // sm_100a code only
+        }
+    }
+    *out = c;
+    return 0;
+}
+
+void imdbn_ctx_destroy(imdbn_ctx* ctx) {
+    if (!ctx) return;
+    tc_destroy(ctx);
+    prof_clear(ctx);
+    if (ctx->arena.base) cudaFree(ctx->arena.base);
+    delete ctx;
+}
+
+const char* imdbn_last_error(imdbn_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int imdbn_set_precision(imdbn_ctx* ctx, int prec) {
+    IMDBN_ARG(ctx, ctx && (prec == IMDBN_PREC_FP32 || prec == IMDBN_PREC_TF32));
+    ctx->precision = prec;
+    return 0;
+}
+
+int64_t imdbn_launch_count(imdbn_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int imdbn_profile_enable(imdbn_ctx* ctx, int enable) {
+    IMDBN_ARG(ctx, ctx != nullptr);
+    prof_clear(ctx);
+    ctx->profile = enable != 0;
+    return 0;
+}
+
+int imdbn_profile_read(imdbn_ctx* ctx, int kind, int V, int H, double* ms_sum, int64_t* count) {
+    IMDBN_ARG(ctx, ctx && ms_sum && count);
+    double sum = 0.0;
+    int64_t n = 0;
+    for (auto& r : ctx->prof) {
+        if (r.kind != kind || r.V != V || r.H != H) continue;
+        IMDBN_CUDA(ctx, cudaEventSynchronize(r.b));
+        float ms = 0.f;
+        IMDBN_CUDA(ctx, cudaEventElapsedTime(&ms, r.a, r.b));
+        sum += ms; ++n;
+    }
+    *ms_sum = sum; *count = n;
+    return 0;
+}
+
+int imdbn_up(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* v, int B, float T, float* p_out,
+             float* s_out, const imdbn_rng* rng, uint32_t draw_u, imdbn_stream stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_rbm(ctx, rbm, false);
+    if (rc) return rc;
+    IMDBN_ARG(ctx, v && B > 0 && (p_out || s_out) && (!s_out || rng));
+    const PassPlan pu = plan_pass(ctx, B, rbm->H, rbm->V);
+    rc = arena_begin(ctx, pad256(pu.part_floats) + tc_ws_bytes(ctx, rbm, B), st);
+    if (rc) return rc;
+    float* part = arena_take<float>(ctx, pu.part_floats);
+    RngKey key{};
+    if (rng) key = make_key(rng);
+    return up_pass(ctx, rbm, v, B, T, p_out, s_out, key, draw_u, pu, part, st);
+}
+
+int imdbn_down(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* h, int B, float T, float* p_out,
+               float* logits_out, float* s_out, const imdbn_rng* rng, uint32_t draw_u,
+               uint32_t draw_cat, imdbn_stream stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_rbm(ctx, rbm, false);
+    if (rc) return rc;
+    IMDBN_ARG(ctx, h && B > 0 && (p_out || s_out || logits_out) && (!s_out || rng));
+    const PassPlan pd = plan_pass(ctx, B, rbm->V, rbm->H);
+    const size_t nBV = (size_t)B * rbm->V;
+    rc = arena_begin(ctx, pad256(pd.part_floats) + pad256(2 * nBV) + tc_ws_bytes(ctx, rbm, B), st);
+    if (rc) return rc;
+    float* part = arena_take<float>(ctx, pd.part_floats);
+    float* lg_tmp = arena_take<float>(ctx, 2 * nBV);
+    RngKey key{};
+    if (rng) key = make_key(rng);
+    return down_pass(ctx, rbm, h, B, T, p_out, logits_out, s_out, lg_tmp, key, draw_u, draw_cat, pd,
+                     part, st);
+}
+
+int imdbn_sample_visible(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* p, int B, float* s_out,
+                         const imdbn_rng* rng, uint32_t draw_u, uint32_t draw_cat,
+                         imdbn_stream stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_rbm(ctx, rbm, false);
+    if (rc) return rc;
+    IMDBN_ARG(ctx, p && s_out && rng && B > 0 && p != s_out);
+    const size_t nBV = (size_t)B * rbm->V;
+    const RngKey key = make_key(rng);
+    rc = arena_begin(ctx, pad256(nBV), st);
+    if (rc) return rc;
+    float* ptmp = arena_take<float>(ctx, nBV);
+    k_bernoulli<<<ew_blocks(nBV, ctx->num_sms), 256, 0, st>>>(p, B, rbm->V, s_out, key, draw_u);
+    IMDBN_CHECK_LAUNCH(ctx, "k_bernoulli");
+    const Groups gr = make_groups(rbm);
+    if (gr.n) {
+        IMDBN_CUDA(ctx, cudaMemcpyAsync(ptmp, p, nBV * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        k_groups<<<(B * gr.n * 32 + 127) / 128, 128, 0, st>>>(nullptr, ptmp, s_out, B, rbm->V, gr, key,
+                                                              draw_cat);
+        IMDBN_CHECK_LAUNCH(ctx, "k_groups");
+    }
+    return 0;
+}
+
+int imdbn_free_energy(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* v, int B, float* F_out,
+                      imdbn_stream stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_rbm(ctx, rbm, false);
+    if (rc) return rc;
+    IMDBN_ARG(ctx, v && F_out && B > 0);
+    const PassPlan pu = plan_pass(ctx, B, rbm->H, rbm->V);
+    rc = arena_begin(ctx, pad256(pu.part_floats) + tc_ws_bytes(ctx, rbm, B), st);
+    if (rc) return rc;
+    float* part = arena_take<float>(ctx, pu.part_floats);
+    rc = gemm_up(ctx, rbm, v, B, pu, part, st);
+    if (rc) return rc;
+    k_free_energy<<<B, 256, 0, st>>>(part, pu.splits, v, B, rbm->V, rbm->H, rbm->hb, rbm->vb, F_out);
+    IMDBN_CHECK_LAUNCH(ctx, "k_free_energy");
+    return 0;
+}
+
+int imdbn_cd_train(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* data, int B, int k,
+                   const imdbn_update* upd, const imdbn_rng* rng, float* loss_out,
+                   imdbn_stream stream) {
+    IMDBN_ARG(ctx, upd && upd->batch_global > 0);
+    return cd_core(ctx, rbm, data, B, k, upd, rng, loss_out, nullptr, (cudaStream_t)stream);
+}
+
+int64_t imdbn_stats_size(const imdbn_rbm* r) {
+    return (int64_t)r->V * r->H + 2 * (int64_t)r->H + r->V + 1;
+}
+
+int imdbn_cd_stats(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* data, int B, int k,
+                   const imdbn_rng* rng, float* stats_out, imdbn_stream stream) {
+    IMDBN_ARG(ctx, stats_out != nullptr);
+    return cd_core(ctx, rbm, data, B, k, nullptr, rng, nullptr, stats_out, (cudaStream_t)stream);
+}
+
+int imdbn_apply_update(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* stats,
+                       const imdbn_update* upd, float* loss_out, imdbn_stream stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_rbm(ctx, rbm, true);
+    if (rc) return rc;
+    IMDBN_ARG(ctx, stats && upd && upd->batch_global > 0);
+    const size_t n = (size_t)rbm->V * rbm->H;
+    k_weight_update<<<ew_blocks(n, ctx->num_sms), 256, 0, st>>>(stats, n, rbm->W, rbm->Wm, upd->lr,
+                                                               upd->momentum, upd->weight_decay,
+                                                               (float)upd->batch_global);
+    IMDBN_CHECK_LAUNCH(ctx, "k_weight_update");
+    return bias_update(ctx, rbm, stats + n, upd, (float)upd->batch_global * rbm->V, loss_out, st);
+}
+
+int imdbn_run_chain(imdbn_ctx* ctx, const imdbn_rbm* rbm, const imdbn_chain* ch, int B,
+                    float* v_out, float* vprob_out, const imdbn_rng* rng, imdbn_stream stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_rbm(ctx, rbm, false);
+    if (rc) return rc;
+    IMDBN_ARG(ctx, ch && v_out && rng && B > 0);
+    rc = arena_begin(ctx, pad256(chain_ws_floats(rbm, ch->n_steps)) + 1024, st);
+    if (rc) return rc;
+    float* Wt = arena_take<float>(ctx, (size_t)rbm->V * rbm->H);
+    float* tables = arena_take<float>(ctx, 3 * (size_t)std::max(1, ch->n_steps));
+    return run_chain(ctx, rbm, ch, B, v_out, vprob_out, make_key(rng), Wt, tables, st);
+}
+
+int imdbn_cd_train_clamped(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* v_known,
+                           const float* known_mask, int B, const imdbn_clamped_cfg* cfg,
+                           const imdbn_update* upd, const imdbn_rng* rng, float* loss_out,
+                           imdbn_stream stream) {
+    IMDBN_ARG(ctx, upd && upd->batch_global > 0);
+    return clamped_core(ctx, rbm, v_known, known_mask, B, cfg, upd, rng, loss_out, nullptr,
+                        (cudaStream_t)stream);
+}
+
+int imdbn_cd_clamped_stats(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* v_known,
+                           const float* known_mask, int B, const imdbn_clamped_cfg* cfg,
+                           const imdbn_rng* rng, float* stats_out, imdbn_stream stream) {
+    IMDBN_ARG(ctx, stats_out != nullptr);
+    return clamped_core(ctx, rbm, v_known, known_mask, B, cfg, nullptr, rng, nullptr, stats_out,
+                        (cudaStream_t)stream);
+}
+
+int imdbn_best_of_k(imdbn_ctx* ctx, const float* cand, const float* F, int K, int B, int V,
+                    float* out, int32_t* idx_out, imdbn_stream stream) {
+    IMDBN_ARG(ctx, cand && F && out && K > 0 && B > 0 && V > 0);
+    k_best_of_k<<<B, 128, 0, (cudaStream_t)stream>>>(cand, F, K, B, V, out, idx_out);
+    IMDBN_CHECK_LAUNCH(ctx, "k_best_of_k");
+    return 0;
+}
+
+int imdbn_class_stats(imdbn_ctx* ctx, const float* z, const float* y, int B, int Dz, int K,
+                      float* sum_z, float* class_sum, float* class_count, float* label_sum,
+                      imdbn_stream stream) {
+    IMDBN_ARG(ctx, z && y && sum_z && class_sum && class_count && label_sum && B > 0 && Dz > 0 && K > 0);
+    const int cols = std::max(Dz, K);
+    k_class_stats<<<(cols + 127) / 128, 128, 0, (cudaStream_t)stream>>>(z, y, B, Dz, K, sum_z, class_sum,
+                                                                      class_count, label_sum);
+    IMDBN_CHECK_LAUNCH(ctx, "k_class_stats");
+    return 0;
+}
+
+int imdbn_random_field(imdbn_ctx* ctx, const imdbn_rng* rng, uint32_t draw, int kind, int rows,
+                       int cols, float* out, imdbn_stream stream) {
+    IMDBN_ARG(ctx, rng && out && rows > 0 && cols > 0);
+    k_random_field<<<ew_blocks((size_t)rows * cols, ctx->num_sms), 256, 0, (cudaStream_t)stream>>>(
+        make_key(rng), draw, kind, rows, cols, out);
+    IMDBN_CHECK_LAUNCH(ctx, "k_random_field");
+    return 0;
+}
+
+}  // extern "C"

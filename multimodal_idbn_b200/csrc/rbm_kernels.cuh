@@ -1,0 +1,291 @@
+// Element-wise / reduction kernels around the GEMMs: the fused bias + temperature + sigmoid +
+// Philox-sampling finishes of the up and down passes, softmax groups, column statistics and the
+// bias updates of CD-k (imdbn/models/rbm.py:81-135, 211-226).
+#pragma once
+#include "common.cuh"
+
+namespace imdbn {
+
+// ---- up pass finish: p = sigmoid((sum_s part + hb)/T), s = (p > U)           rbm.py:92,175,203
+__global__ void k_finish_up(const float* __restrict__ part, int splits, int B, int H,
+                            const float* __restrict__ hb, float T, float* __restrict__ p_out,
+                            float* __restrict__ s_out, RngKey key, uint32_t draw_u) {
+    const size_t n = (size_t)B * H;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(i / H), j = (int)(i % H);
+        float x = 0.0f;
+        for (int s = 0; s < splits; ++s) x += part[(size_t)s * n + i];
+        x = add_rn(x, hb[j]) / T;
+        const float p = sigmoidf_ref(x);
+        if (p_out) p_out[i] = p;
+        if (s_out) s_out[i] = (p > rf_uniform(key, draw_u, b, j)) ? 1.0f : 0.0f;
+    }
+}
+
+// ---- down pass finish: logits = (sum_s part + vb)/T, p = sigmoid(logits), s = (p > U)
+//      (softmax groups are overwritten afterwards by k_groups)                 rbm.py:96,110,125
+__global__ void k_finish_down(const float* __restrict__ part, int splits, int B, int V,
+                              const float* __restrict__ vb, float T, float* __restrict__ p_out,
+                              float* __restrict__ logits_out, float* __restrict__ s_out,
+                              RngKey key, uint32_t draw_u) {
+    const size_t n = (size_t)B * V;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(i / V), c = (int)(i % V);
+        float x = 0.0f;
+        for (int s = 0; s < splits; ++s) x += part[(size_t)s * n + i];
+        x = add_rn(x, vb[c]) / T;
+        if (logits_out) logits_out[i] = x;
+        const float p = sigmoidf_ref(x);
+        if (p_out) p_out[i] = p;
+        if (s_out) s_out[i] = (p > rf_uniform(key, draw_u, b, c)) ? 1.0f : 0.0f;
+    }
+}
+
+// Bernoulli part of sample_visible on given probabilities                       rbm.py:125
+__global__ void k_bernoulli(const float* __restrict__ p, int B, int V, float* __restrict__ s_out,
+                            RngKey key, uint32_t draw_u) {
+    const size_t n = (size_t)B * V;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(i / V), c = (int)(i % V);
+        s_out[i] = (p[i] > rf_uniform(key, draw_u, b, c)) ? 1.0f : 0.0f;
+    }
+}
+
+// One warp per (row, group): softmax of the logits over [s,e) written over p (rbm.py:113-114) and,
+// if s_out, the one-hot categorical draw of sample_visible (rbm.py:129-133): q = clamp(p,1e-8,1),
+// q /= sum q, idx = #{j: cdf_j <= u} with a sequential fp32 cdf (oracle.categorical_index).
+// With logits == nullptr the probabilities already in p are used (sample_visible on a given p).
+__global__ void k_groups(const float* __restrict__ logits, float* __restrict__ p, float* __restrict__ s_out,
+                         int B, int V, Groups gr, RngKey key, uint32_t draw_cat) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= B * gr.n) return;
+    const int b = warp / gr.n, g = warp % gr.n;
+    const int s = gr.s[g], e = gr.e[g];
+    const size_t row = (size_t)b * V;
+    if (logits) {
+        float mx = -INFINITY;
+        for (int c = s + lane; c < e; c += 32) mx = fmaxf(mx, logits[row + c]);
+        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.0f;
+        for (int c = s + lane; c < e; c += 32) sum += expf(logits[row + c] - mx);
+        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        for (int c = s + lane; c < e; c += 32) p[row + c] = expf(logits[row + c] - mx) / sum;
+        __syncwarp();
+    }
+    if (s_out && lane == 0) {
+        float tot = 0.0f;
+        for (int c = s; c < e; ++c) tot += fminf(fmaxf(p[row + c], 1e-8f), 1.0f);
+        const float u = rf_uniform(key, draw_cat, b, g);
+        float cdf = 0.0f;
+        int idx = 0;
+        for (int c = s; c < e; ++c) {
+            cdf += fminf(fmaxf(p[row + c], 1e-8f), 1.0f) / tot;
+            idx += (cdf <= u) ? 1 : 0;
+        }
+        idx = min(idx, e - s - 1);
+        for (int c = s; c < e; ++c) s_out[row + c] = (c - s == idx) ? 1.0f : 0.0f;
+    }
+}
+
+// ---- column statistics of one CD step (rbm.py:216,223,226 / 478,480,483), one thread per column:
+//   out = [ dh (H) | dv (V) | pos_h column sum (H) | squared error (1) ]
+//   dh = sum_b hp - sum_b hn ; dv = sum_b vp - sum_b vn ; sq = sum (ea - eb)^2 over [B,V]
+__global__ void k_colstats(const float* __restrict__ hp, const float* __restrict__ hn,
+                           const float* __restrict__ vp, const float* __restrict__ vn,
+                           const float* __restrict__ ea, const float* __restrict__ eb, int B, int V,
+                           int H, float* __restrict__ out, float* __restrict__ sq_part) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    float sq = 0.0f;
+    if (c < H) {
+        float a = 0.0f, n = 0.0f;
+        for (int b = 0; b < B; ++b) { a += hp[(size_t)b * H + c]; n += hn[(size_t)b * H + c]; }
+        out[c] = a - n;
+        out[H + V + c] = a;
+    }
+    if (c < V) {
+        float a = 0.0f, n = 0.0f;
+        for (int b = 0; b < B; ++b) {
+            const size_t o = (size_t)b * V + c;
+            a += vp[o]; n += vn[o];
+            const float d = ea[o] - eb[o];
+            sq = fmaf(d, d, sq);
+        }
+        out[H + c] = a - n;
+    }
+    // deterministic block sum of the squared error -> one partial per block
+    __shared__ float red[32];
+    for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0f;
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) sq_part[blockIdx.x] = v;
+    }
+}
+
+// sum the per-block partials in index order (single block)
+__global__ void k_sum_partials(const float* __restrict__ part, int n, float* __restrict__ out) {
+    __shared__ float red[32];
+    float v = 0.0f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) v += part[i];
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0f;
+        for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0) *out = t;
+    }
+}
+
+// ---- bias updates (rbm.py:216-224 / 478-481) and the loss (rbm.py:226 / 483)
+__global__ void k_bias_update(const float* __restrict__ st, int V, int H, float* __restrict__ hb,
+                              float* __restrict__ hbm, float* __restrict__ vb, float* __restrict__ vbm,
+                              float lr, float mom, float bsz, int sparsity, float sp_target,
+                              float n_loss, float* __restrict__ loss_out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < H) {
+        float m = add_rn(mul_rn(hbm[c], mom), mul_rn(lr, st[c]) / bsz);
+        if (sparsity) m = add_rn(m, mul_rn(-lr, add_rn(st[H + V + c] / bsz, -sp_target)));
+        hbm[c] = m;
+        hb[c] = add_rn(hb[c], m);
+    }
+    if (c < V) {
+        const float m = add_rn(mul_rn(vbm[c], mom), mul_rn(lr, st[H + c]) / bsz);
+        vbm[c] = m;
+        vb[c] = add_rn(vb[c], m);
+    }
+    if (c == 0 && loss_out) *loss_out = st[2 * H + V] / n_loss;
+}
+
+// element-wise weight update from an (all-reduced) dS                          rbm.py:212-213
+__global__ void k_weight_update(const float* __restrict__ dS, size_t n, float* __restrict__ W,
+                                float* __restrict__ Wm, float lr, float mom, float wd, float bsz) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const float w = W[i];
+        const float grad = add_rn(dS[i] / bsz, -mul_rn(wd, w));
+        const float wm = add_rn(mul_rn(Wm[i], mom), mul_rn(lr, grad));
+        Wm[i] = wm;
+        W[i] = add_rn(w, wm);
+    }
+}
+
+// v = a*(1-km) + known*km                                                      rbm.py:465
+__global__ void k_clampmix(const float* __restrict__ a, const float* __restrict__ known,
+                           const float* __restrict__ km, size_t n, float* __restrict__ out) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x)
+        out[i] = clampmix(a[i], known[i], km[i]);
+}
+
+// ---- free energy finish (energy_utils.py:25-28): F[b] = -v.b_v - sum_j softplus(pre_j)
+__global__ void k_free_energy(const float* __restrict__ part, int splits, const float* __restrict__ v,
+                              int B, int V, int H, const float* __restrict__ hb,
+                              const float* __restrict__ vb, float* __restrict__ F) {
+    const int b = blockIdx.x;
+    const size_t n = (size_t)B * H;
+    float th = 0.0f, tv = 0.0f;
+    for (int j = threadIdx.x; j < H; j += blockDim.x) {
+        float x = 0.0f;
+        for (int s = 0; s < splits; ++s) x += part[(size_t)s * n + (size_t)b * H + j];
+        x = add_rn(x, hb[j]);
+        th += (x > 20.0f) ? x : log1pf(expf(x));   // torch softplus, threshold 20
+    }
+    for (int c = threadIdx.x; c < V; c += blockDim.x) tv = fmaf(v[(size_t)b * V + c], vb[c], tv);
+    __shared__ float r1[32], r2[32];
+    for (int o = 16; o; o >>= 1) {
+        th += __shfl_xor_sync(0xffffffffu, th, o);
+        tv += __shfl_xor_sync(0xffffffffu, tv, o);
+    }
+    if ((threadIdx.x & 31) == 0) { r1[threadIdx.x >> 5] = th; r2[threadIdx.x >> 5] = tv; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.0f, c = 0.0f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += r1[w]; c += r2[w]; }
+        F[b] = -c - a;
+    }
+}
+
+// ---- best-of-K pick (imdbn.py:472-474): first minimum wins
+__global__ void k_best_of_k(const float* __restrict__ cand, const float* __restrict__ F, int K, int B,
+                            int V, float* __restrict__ out, int32_t* __restrict__ idx_out) {
+    const int b = blockIdx.x;
+    int best = 0;
+    float fb = F[b];
+    for (int k = 1; k < K; ++k) {
+        const float f = F[(size_t)k * B + b];
+        if (f < fb) { fb = f; best = k; }
+    }
+    for (int c = threadIdx.x; c < V; c += blockDim.x)
+        out[(size_t)b * V + c] = cand[((size_t)best * B + b) * V + c];
+    if (threadIdx.x == 0 && idx_out) idx_out[b] = best;
+}
+
+// ---- per-class sums (imdbn.py:249-251, 271-277): one thread per latent column, rows in order
+__global__ void k_class_stats(const float* __restrict__ z, const float* __restrict__ y, int B, int Dz,
+                              int K, float* __restrict__ sum_z, float* __restrict__ class_sum,
+                              float* __restrict__ class_count, float* __restrict__ label_sum) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < Dz) {
+        float s = 0.0f;
+        for (int b = 0; b < B; ++b) {
+            const float zv = z[(size_t)b * Dz + d];
+            s += zv;
+            int arg = 0;
+            float best = y[(size_t)b * K];
+            for (int k = 1; k < K; ++k) {
+                const float yv = y[(size_t)b * K + k];
+                if (yv > best) { best = yv; arg = k; }
+            }
+            class_sum[(size_t)arg * Dz + d] += zv;
+        }
+        sum_z[d] += s;
+    }
+    if (d < K) {
+        float cnt = 0.0f, ls = 0.0f;
+        for (int b = 0; b < B; ++b) {
+            int arg = 0;
+            float best = y[(size_t)b * K];
+            for (int k = 1; k < K; ++k) {
+                const float yv = y[(size_t)b * K + k];
+                if (yv > best) { best = yv; arg = k; }
+            }
+            cnt += (arg == d) ? 1.0f : 0.0f;
+            ls += y[(size_t)b * K + d];
+        }
+        class_count[d] += cnt;
+        label_sum[d] += ls;
+    }
+}
+
+__global__ void k_random_field(RngKey key, uint32_t draw, int kind, int rows, int cols,
+                               float* __restrict__ out) {
+    const size_t n = (size_t)rows * cols;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / cols), c = (int)(i % cols);
+        out[i] = kind ? rf_normal(key, draw, r, c) : rf_uniform(key, draw, r, c);
+    }
+}
+
+__global__ void k_transpose(const float* __restrict__ in, int R, int C, float* __restrict__ out) {
+    __shared__ float t[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        t[i][threadIdx.x] = (r < R && c < C) ? in[(size_t)r * C + c] : 0.0f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (r < R && c < C) out[(size_t)c * R + r] = t[threadIdx.x][i];
+    }
+}
+
+}  // namespace imdbn

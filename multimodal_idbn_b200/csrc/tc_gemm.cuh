@@ -1,0 +1,20 @@
+// Tensor-core (tcgen05 / TMEM / TMA) path of the GEMM-shaped passes: interface used by
+// imdbn_b200.cu.  Implemented in tc_gemm.cu.
+#pragma once
+#include "common.cuh"
+
+namespace imdbn {
+
+bool tc_up_supported(const imdbn_ctx* ctx, const imdbn_rbm* r, int B);
+bool tc_down_supported(const imdbn_ctx* ctx, const imdbn_rbm* r, int B);
+bool tc_stats_supported(const imdbn_ctx* ctx, const imdbn_rbm* r, int B);
+size_t tc_ws_bytes(const imdbn_ctx* ctx, const imdbn_rbm* r, int B);
+
+int tc_gemm_up(imdbn_ctx* ctx, const imdbn_rbm* r, const float* v, int B, float* part, cudaStream_t st);
+int tc_gemm_down(imdbn_ctx* ctx, const imdbn_rbm* r, const float* h, int B, float* part, cudaStream_t st);
+int tc_gemm_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* vp, const float* hp,
+                  const float* vn, const float* hn, int B, float* dS_out, const imdbn_update* upd,
+                  cudaStream_t st);
+void tc_destroy(imdbn_ctx* ctx);
+
+}  // namespace imdbn

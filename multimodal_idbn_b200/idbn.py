@@ -1,0 +1,201 @@
+"""Drop-in ``iDBN`` (reference ``imdbn/models/idbn.py``): a stack of CUDA-backed RBMs.
+
+Hot loop = ``train`` (idbn.py:195-204): per minibatch every layer takes one CD-k update and the
+batch is pushed through the *updated* layer.  Here the loop issues no host synchronisation: losses
+stay on the device until the end of the epoch, and the next minibatch is copied host->device on a
+side stream while the current one trains.  ``represent`` / ``reconstruct`` / ``decode`` are chains
+of up / down passes; ``save_model`` writes the reference's ``{"layers", "params"}`` pickle.
+
+W&B visualisation (PCA plots, probes: idbn.py:207-305) is out of scope; only the scalar loss is
+logged when a ``wandb_run`` is given.
+"""
+from __future__ import annotations
+
+import os
+import pickle
+from typing import Iterable, List, Optional
+
+import torch
+
+from .rbm import RBM
+
+
+def _flat(x: torch.Tensor, device) -> torch.Tensor:
+    """``img.to(device).view(B, -1).float()`` (idbn.py:200,319,336)."""
+    x = x.to(device, non_blocking=True)
+    return x.reshape(x.size(0), -1).float()
+
+
+def prefetch_to_device(loader: Iterable, device):
+    """Yield the loader's batches already on ``device``: batch i+1 is copied on a side stream while
+    the caller works on batch i.  Falls back to plain iteration on CPU devices."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        for batch in loader:
+            yield batch
+        return
+    copy_stream = torch.cuda.Stream(device=device)
+    main = torch.cuda.current_stream(device)
+
+    def stage(batch):
+        with torch.cuda.stream(copy_stream):
+            moved = tuple(b.to(device, non_blocking=True) if torch.is_tensor(b) else b for b in batch)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return moved, ev
+
+    it = iter(loader)
+    try:
+        cur = stage(next(it))
+    except StopIteration:
+        return
+    while cur is not None:
+        try:
+            nxt = stage(next(it))
+        except StopIteration:
+            nxt = None
+        moved, ev = cur
+        main.wait_event(ev)
+        for b in moved:
+            if torch.is_tensor(b):
+                b.record_stream(main)
+        yield moved
+        cur = nxt
+
+
+class iDBN:
+    """Image deep belief network: ``layers`` is a list of :class:`RBM` (idbn.py:39-161)."""
+
+    def __init__(self, layer_sizes: List[int], params: dict, dataloader, val_loader, device,
+                 wandb_run=None, logging_config_path: Optional[str] = None):
+        self.layers: List[RBM] = []
+        self.params = params
+        self.dataloader = dataloader
+        self.val_loader = val_loader
+        self.device = torch.device(device) if device is not None else torch.device(
+            "cuda" if torch.cuda.is_available() else "cpu")
+        self.wandb_run = wandb_run
+
+        self.logging_cfg = {}
+        try:                                                      # idbn.py:98-110
+            import yaml
+            from pathlib import Path
+            cfg_path = Path(logging_config_path) if logging_config_path else Path(
+                "src/configs/logging_config.yaml")
+            if cfg_path.exists():
+                with cfg_path.open("r") as f:
+                    cfg = yaml.safe_load(f)
+                if isinstance(cfg, dict):
+                    self.logging_cfg = cfg
+        except Exception:
+            pass
+
+        self.text_flag = False
+        self.arch_str = "-".join(map(str, layer_sizes))
+        self.arch_dir = os.path.join("logs-idbn", f"architecture_{self.arch_str}")
+        try:
+            os.makedirs(self.arch_dir, exist_ok=True)             # idbn.py:115-116
+        except OSError:
+            pass
+
+        self.cd_k = int(self.params.get("CD", 1))
+        self.sparsity_last = bool(self.params.get("SPARSITY", False))
+        self.sparsity_factor = float(self.params.get("SPARSITY_FACTOR", 0.1))
+
+        try:
+            self.val_batch, self.val_labels = next(iter(val_loader))
+        except Exception:
+            self.val_batch, self.val_labels = None, None
+
+        self.features = None
+        try:                                                      # idbn.py:130-146
+            indices = val_loader.dataset.indices
+            base = val_loader.dataset.dataset
+            feats = {
+                "Cumulative Area": torch.tensor([base.cumArea_list[i] for i in indices], dtype=torch.float32),
+                "Convex Hull": torch.tensor([base.CH_list[i] for i in indices], dtype=torch.float32),
+                "Labels": torch.tensor([base.labels[i] for i in indices], dtype=torch.float32),
+            }
+            dens = getattr(base, "density_list", None)
+            if dens is not None:
+                feats["Density"] = torch.tensor([dens[i] for i in indices], dtype=torch.float32)
+            self.features = feats
+        except Exception:
+            pass
+
+        n = len(layer_sizes) - 1
+        for i in range(n):                                        # idbn.py:149-161
+            self.layers.append(RBM(
+                num_visible=layer_sizes[i], num_hidden=layer_sizes[i + 1],
+                learning_rate=self.params["LEARNING_RATE"],
+                weight_decay=self.params["WEIGHT_PENALTY"],
+                momentum=self.params["INIT_MOMENTUM"],
+                dynamic_lr=self.params["LEARNING_RATE_DYNAMIC"],
+                final_momentum=self.params["FINAL_MOMENTUM"],
+                sparsity=(self.sparsity_last and i == n - 1),
+                sparsity_factor=self.sparsity_factor,
+            ).to(self.device))
+        self.loss_history: List[float] = []
+
+    def _layers_to_monitor(self) -> List[int]:
+        layers = {len(self.layers)}
+        if len(self.layers) > 1:
+            layers.add(1)
+        return sorted(layers)
+
+    def _layer_tag(self, idx: int) -> str:
+        return f"layer{idx}"
+
+    # ------------------------------------------------------------------ training
+    @torch.no_grad()
+    def train_step(self, v: torch.Tensor, epoch: int, epochs: int) -> List[torch.Tensor]:
+        """One minibatch of the hot loop (idbn.py:200-204); returns the per-layer losses as device
+        scalars (no host synchronisation)."""
+        v = _flat(v, self.device)
+        losses = []
+        for rbm in self.layers:
+            losses.append(rbm.train_epoch(v, epoch, epochs, CD=self.cd_k))
+            v = rbm.forward(v)
+        return losses
+
+    def train(self, epochs: int, log_every_pca: int = 25, log_every_probe: int = 10):
+        """Layer-interleaved CD training (idbn.py:179-305).  ``loss_history`` receives the mean
+        loss of every epoch (one device->host read per epoch)."""
+        for epoch in range(int(epochs)):
+            losses: List[torch.Tensor] = []
+            for batch in prefetch_to_device(self.dataloader, self.device):
+                losses.extend(self.train_step(batch[0], epoch, epochs))
+            if losses:
+                mean_loss = float(torch.stack(losses).mean())
+                self.loss_history.append(mean_loss)
+                if self.wandb_run:
+                    self.wandb_run.log({"idbn/loss": mean_loss, "epoch": epoch})
+
+    # ------------------------------------------------------------------ inference chains
+    @torch.no_grad()
+    def represent(self, x: torch.Tensor, upto_layer: Optional[int] = None) -> torch.Tensor:
+        """idbn.py:307-323."""
+        v = _flat(x, self.device)
+        L = len(self.layers) if upto_layer is None else max(0, min(len(self.layers), int(upto_layer)))
+        for i in range(L):
+            v = self.layers[i].forward(v)
+        return v
+
+    @torch.no_grad()
+    def reconstruct(self, x: torch.Tensor) -> torch.Tensor:
+        """idbn.py:325-344."""
+        return self.decode(self.represent(x))
+
+    @torch.no_grad()
+    def decode(self, top: torch.Tensor) -> torch.Tensor:
+        """idbn.py:346-359."""
+        cur = top.to(self.device)
+        for rbm in reversed(self.layers):
+            cur = rbm.backward(cur)
+        return cur
+
+    def save_model(self, path: str):
+        """``{"layers": [...], "params": ...}`` pickle (idbn.py:361-373)."""
+        with open(path, "wb") as f:
+            pickle.dump({"layers": self.layers, "params": self.params}, f)
+        print(f"[iDBN] Model saved to {path}")

@@ -1,0 +1,372 @@
+"""GPU parity: the CUDA path (through the C ABI, via the drop-in classes) against
+(a) the golden fixtures produced by the UNMODIFIED reference and (b) the CPU oracle on seeded inputs,
+both fed the same Philox random field.
+
+Tolerances (north_star): sampled binary / one-hot states bit-exact except units whose probability is
+within 1e-6 of the uniform they are compared with; activations / weights within 2e-5 absolute-or-
+relative in fp32 parity mode (different summation order than MKL, nothing else)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import rbm_oracle as O
+from oracle.philox import RandomField
+
+pytestmark = pytest.mark.gpu
+
+TOL = dict(rtol=2e-5, atol=2e-6)
+DEV = "cuda"
+
+
+def T(a):
+    return torch.from_numpy(np.array(a))
+
+
+@pytest.fixture(scope="module")
+def M():
+    import multimodal_idbn_b200 as m
+    m.load_library()
+    m.set_precision("fp32")
+    return m
+
+
+def gpu_rbm(M, g, prefix, groups=(), hyper=None, **kw):
+    W = T(g[prefix + "W"])
+    cfg = dict(learning_rate=0.1, weight_decay=1e-4, momentum=0.5, dynamic_lr=True, final_momentum=0.95)
+    if hyper is not None:
+        lr, wd, mom, fmom, dyn, sp, spf = [float(x) for x in hyper]
+        cfg = dict(learning_rate=lr, weight_decay=wd, momentum=mom, dynamic_lr=bool(dyn),
+                   final_momentum=fmom, sparsity=bool(sp), sparsity_factor=spf)
+    cfg.update(kw)
+    gl = [tuple(int(x) for x in r) for r in np.array(groups).reshape(-1, 2)]
+    r = M.RBM(W.shape[0], W.shape[1], softmax_groups=gl, **cfg).to(DEV)
+    load_params(r, g, prefix)
+    return r
+
+
+def load_params(r, g, prefix):
+    with torch.no_grad():
+        r.W.data.copy_(T(g[prefix + "W"])); r.hid_bias.data.copy_(T(g[prefix + "hb"]))
+        r.vis_bias.data.copy_(T(g[prefix + "vb"]))
+        r.W_m = T(g[prefix + "Wm"]).to(DEV); r.hb_m = T(g[prefix + "hbm"]).to(DEV)
+        r.vb_m = T(g[prefix + "vbm"]).to(DEV)
+
+
+def check_params(r, g, prefix, tol=TOL):
+    for name, t in (("W", r.W), ("hb", r.hid_bias), ("vb", r.vis_bias), ("Wm", r.W_m),
+                    ("hbm", r.hb_m), ("vbm", r.vb_m)):
+        torch.testing.assert_close(t.detach().cpu(), T(g[prefix + name]),
+                                   msg=lambda m, n=name: f"{prefix}{n}: {m}", **tol)
+
+
+def close(a, b, tol=TOL):
+    torch.testing.assert_close(a.detach().cpu(), b if torch.is_tensor(b) else T(b), **tol)
+
+
+# ------------------------------------------------------------------------------ random field
+def test_random_field_matches_host_philox(M):
+    from multimodal_idbn_b200 import _lib as L
+    for seed, stream, row0 in [(20240611, 0, 0), (2 ** 63 + 12345, 77, 4096)]:
+        rng = L.RngStruct(seed, stream, row0)
+        f = RandomField(seed, stream)
+        u = M.random_field(rng, 3, 50, 37, DEV).cpu().numpy()
+        np.testing.assert_array_equal(u, f.uniform(3, 50, 37, row0=row0))      # bit-exact
+        n = M.random_field(rng, 9, 50, 37, DEV, normal=True).cpu().numpy()
+        np.testing.assert_allclose(n, f.normal(9, 50, 37, row0=row0), rtol=0, atol=2e-6)
+
+
+# ------------------------------------------------------------------------------ golden fixtures
+def test_passes_golden(M):
+    g = load_golden("passes")
+    r = gpu_rbm(M, g, "in_", g["groups"])
+    v, h = T(g["v"]).to(DEV), T(g["h"]).to(DEV)
+    close(r.forward(v), g["up_T1"]); close(r.forward(v, T=2.5), g["up_T25"])
+    close(r.visible_probs(h), g["down_T1"]); close(r.visible_probs(h, T=2.5), g["down_T25"])
+    close(r.backward(h, return_logits=True), g["logits"]); close(r.backward(h), g["backward"])
+    close(M.rbm_free_energy(r, v), g["free_energy"], dict(rtol=2e-5, atol=2e-5))
+
+
+@pytest.mark.parametrize("name", ["cd_plain", "cd_sparse", "cd_group"])
+def test_train_epoch_golden(M, name):
+    g = load_golden(name)
+    r = gpu_rbm(M, g, "in_", g["groups"], g["hyper"])
+    data = T(g["data"]).to(DEV)
+    for i, (cd, ep) in enumerate(zip(g["cds"], g["epochs"])):
+        r.set_rng(int(g["seed"]), i)
+        loss = r.train_epoch(data, int(ep), 10, CD=int(cd))
+        check_params(r, g, f"step{i}_")
+        close(loss, g[f"step{i}_loss"])
+
+
+def test_noisy_meanfield_golden(M):
+    g = load_golden("noisy_mf")
+    r = gpu_rbm(M, g, "in_", g["groups"])
+    seed = int(g["seed"])
+    vk, km, mu = (T(g[k]).to(DEV) for k in ("v_known", "km", "mu"))
+    tol = dict(rtol=5e-5, atol=5e-6)
+    r._mu_pull = {"mu_k": mu, "eta0": 0.15}
+    r.set_rng(seed, 0)
+    a = r.noisy_meanfield_annealed(vk, km, n_steps=12)
+    close(a, g["a"], tol)
+    r.set_rng(seed, 1)
+    b = r.noisy_meanfield_annealed(T(g["a"]).to(DEV), km, n_steps=1, T0=0.9, T1=0.9, sigma0=0.0,
+                                   hot_frac=0.0, sharpen_last=0, T_cold_plus=0.9)
+    close(b, g["b"], tol)
+    r._mu_pull = None
+    r.set_rng(seed, 2)
+    c = r.noisy_meanfield_annealed(T(g["v_known2"]).to(DEV), T(g["km2"]).to(DEV), n_steps=10,
+                                   sharpen_last=2)
+    close(c, g["c"], tol)
+
+
+def test_conditional_gibbs_golden(M):
+    from multimodal_idbn_b200.conditional_steps import _gibbs_conditional_step
+    g = load_golden("cond_gibbs")
+    r = gpu_rbm(M, g, "in_", g["groups"])
+    seed = int(g["seed"])
+    vk, km = T(g["v_known"]).to(DEV), T(g["km"]).to(DEV)
+    tol = dict(rtol=5e-5, atol=5e-6)
+    for i, (n, sh, sv) in enumerate(g["cfg"]):
+        r.set_rng(seed, i)
+        out = r.conditional_gibbs(vk, km, n_steps=int(n), sample_h=bool(sh), sample_v=bool(sv))
+        close(out, g[f"out{i}"], tol)
+    v0 = T(g["step_v0"]).to(DEV)
+    r.set_rng(seed, 9)
+    vn, vp = _gibbs_conditional_step(r, v0, vk, km, sample_h=True, sample_v=True)
+    close(vn, g["step_next"], tol); close(vp, g["step_prob"], tol)
+    vn, vp = _gibbs_conditional_step(r, v0, vk, km)
+    close(vn, g["step_next_mf"], tol); close(vp, g["step_prob_mf"], tol)
+
+
+def test_train_epoch_clamped_golden(M):
+    g = load_golden("cd_clamped")
+    r = gpu_rbm(M, g, "in_", g["groups"], g["hyper"])
+    vk, km = T(g["v_known"]).to(DEV), T(g["km"]).to(DEV)
+    tol = dict(rtol=1e-4, atol=1e-5)
+    for i, (cd, c, sh, sv, rc, noisy, ep) in enumerate(g["cfg"]):
+        r.set_rng(int(g["seed"]), i)
+        loss = r.train_epoch_clamped(vk, km, int(ep), 10, CD=int(cd), cond_init_steps=int(c),
+                                     sample_h=bool(sh), sample_v=bool(sv), reclamp_negative=bool(rc),
+                                     aux_lr_mult=0.3, use_noisy_init=bool(noisy))
+        check_params(r, g, f"step{i}_", tol)
+        close(loss, g[f"step{i}_loss"], tol)
+
+
+PARAMS = dict(LEARNING_RATE=0.1, WEIGHT_PENALTY=1e-4, INIT_MOMENTUM=0.5, FINAL_MOMENTUM=0.95,
+              LEARNING_RATE_DYNAMIC=True, CD=1, JOINT_LEARNING_RATE=0.04, JOINT_CD=1,
+              CROSS_GIBBS_STEPS=6, JOINT_AUX_COND_STEPS=4, SPARSITY=True, SPARSITY_FACTOR=0.1)
+
+
+def _loader(x, y, bs):
+    return torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, y), batch_size=bs, shuffle=False)
+
+
+def test_idbn_golden(M, tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    g = load_golden("idbn")
+    x, y = T(g["x"]), T(g["y"])
+    dl = _loader(x, y, int(g["batch"]))
+    m = M.iDBN([40, 20, 10], dict(PARAMS), dl, dl, torch.device(DEV))
+    for i, r in enumerate(m.layers):
+        load_params(r, g, f"in_l{i}_")
+        r.set_rng(int(g["seed"]) + i, 0)
+    m.train(int(g["epochs"]))
+    tol = dict(rtol=5e-5, atol=5e-6)
+    for i, r in enumerate(m.layers):
+        check_params(r, g, f"out_l{i}_", tol)
+    close(m.represent(x), g["represent"], tol); close(m.represent(x, upto_layer=1), g["represent1"], tol)
+    close(m.reconstruct(x), g["reconstruct"], tol)
+    close(m.decode(T(g["decode_in"])), g["decode"], tol)
+    assert len(m.loss_history) == int(g["epochs"])
+    # checkpoint round trip in the reference's format
+    m.save_model(str(tmp_path / "idbn.pkl"))
+    import pickle
+    with open(tmp_path / "idbn.pkl", "rb") as f:
+        d = pickle.load(f)
+    assert set(d) == {"layers", "params"} and len(d["layers"]) == 2
+    close(d["layers"][0].forward(x.view(x.size(0), -1).to(DEV)), m.layers[0].forward(x.view(x.size(0), -1).to(DEV)).cpu())
+
+
+def test_imdbn_golden(M, tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    g = load_golden("imdbn")
+    K = int(g["K"])
+    x, y = T(g["x"]), T(g["y"])
+    dl = _loader(x, y, int(g["batch"]))
+    m = M.iMDBN([40, 20, 10], 8, params=dict(PARAMS), dataloader=dl, val_loader=dl,
+                device=torch.device(DEV), num_labels=K)
+    for i, r in enumerate(m.image_idbn.layers):
+        load_params(r, g, f"in_l{i}_")
+    load_params(m.joint_rbm, g, "in_joint_")
+    tol = dict(rtol=1e-4, atol=1e-5)
+    m.init_joint_bias_from_data(n_batches=2)
+    close(m.joint_rbm.vis_bias, g["bias_vb"], tol)
+    close(m.z_class_mean, g["z_class_mean"], tol); close(m.z_class_count, g["z_class_count"], tol)
+    close(m.represent((x, y)), g["represent"], tol)
+
+    z = m.image_idbn.represent(x)
+    m.joint_rbm.set_rng(int(g["seed"]) + 100, 0)
+    img, py = m._cross_reconstruct(z, y.to(DEV), steps=6)
+    close(img, g["cross_img"], tol); close(py, g["cross_py"], tol)
+    assert m.joint_rbm._rng_stream == 6
+    M.RBM.free_energy = M.rbm_free_energy          # live best-of-K
+    try:
+        img, py = m._cross_reconstruct(z, y.to(DEV), steps=6)
+    finally:
+        del M.RBM.free_energy
+    close(img, g["cross_img_fe"], tol); close(py, g["cross_py_fe"], tol)
+
+    m.train_joint(int(g["train_epochs"]))
+    assert m.joint_rbm._rng_stream == int(g["final_stream"])
+    # 30 dependent updates of a chaotic-ish map: compare with a looser tolerance
+    check_params(m.joint_rbm, g, "out_joint_", dict(rtol=2e-3, atol=2e-4))
+    assert len(m.metrics_history) == int(g["train_epochs"])
+
+    m.save_model(str(tmp_path / "m.pkl"))
+    d = M.iMDBN.load_model(str(tmp_path / "m.pkl"), device=torch.device(DEV))
+    for key in ("layers", "params", "image_idbn", "joint_rbm", "num_labels", "Dz_img", "arch_str",
+                "features", "metadata", "z_class_mean"):
+        assert key in d
+    assert len(d["layers"]) == 3 and d["metadata"]["model_type"] == "iMDBN"
+
+
+# ------------------------------------------------------------------------------ oracle at size
+def oracle_and_gpu(M, V, H, groups=None, seed=0, scale=1.0, **hyper):
+    st = O.new_state(V, H, seed=seed, groups=groups, **hyper)
+    st.W *= scale
+    g = torch.Generator().manual_seed(seed + 1)
+    st.hb.copy_(torch.randn(H, generator=g) * 0.1); st.vb.copy_(torch.randn(V, generator=g) * 0.1)
+    r = M.RBM(V, H, st.lr, st.weight_decay, st.momentum, dynamic_lr=st.dynamic_lr,
+              final_momentum=st.final_momentum, sparsity=st.sparsity,
+              sparsity_factor=st.sparsity_factor, softmax_groups=list(groups or [])).to(DEV)
+    with torch.no_grad():
+        r.W.data.copy_(st.W); r.hid_bias.data.copy_(st.hb); r.vis_bias.data.copy_(st.vb)
+    return st, r
+
+
+@pytest.mark.parametrize("B", [1, 7, 64, 130])
+def test_up_sample_bit_exact_outside_1e6_band(M, B):
+    """C1 shape: every sampled hidden unit equals the oracle's except where |p - u| <= 1e-6."""
+    from multimodal_idbn_b200 import _lib as L
+    V, H = 10000, 1500
+    st, r = oracle_and_gpu(M, V, H, seed=3)
+    v = O.synthetic_images(B, V, seed=5)
+    f = RandomField(99, 4)
+    p_ref = O.hidden_probs(st, v)
+    u = torch.from_numpy(f.uniform(0, B, H))
+    s_ref = (p_ref > u).float()
+    p, s = r._up(v.to(DEV), 1.0, sample=True, rng=L.RngStruct(99, 4, 0), draw=0)
+    close(p, p_ref, dict(rtol=0, atol=2e-6))
+    diff = (s.cpu() != s_ref)
+    assert int((diff & ((p_ref - u).abs() > 1e-6)).sum()) == 0
+    assert int(diff.sum()) <= 2
+
+
+def test_down_sample_and_categorical_at_joint_shape(M):
+    from multimodal_idbn_b200 import _lib as L
+    V, H, B = 532, 256, 64
+    st, r = oracle_and_gpu(M, V, H, groups=[(500, 532)], seed=4, scale=3.0)
+    h = (torch.rand(B, H, generator=torch.Generator().manual_seed(1)) < 0.5).float()
+    f = RandomField(7, 1)
+    p_ref = O.visible_probs(st, h)
+    u = torch.from_numpy(f.uniform(1, B, V))
+    s_ref = O.sample_visible(st, p_ref, u, [torch.from_numpy(f.cat_uniform(2, B, 0))])
+    p, _, s = r._down(h.to(DEV), 1.0, sample=True, rng=L.RngStruct(7, 1, 0), draw_u=1, draw_cat=2)
+    close(p, p_ref, dict(rtol=0, atol=2e-6))
+    assert torch.allclose(p[:, 500:].sum(1).cpu(), torch.ones(B), atol=1e-5)
+    assert torch.equal(s[:, 500:].sum(1).cpu(), torch.ones(B))                 # one-hot
+    assert torch.equal(s[:, 500:].argmax(1).cpu(), s_ref[:, 500:].argmax(1))   # same class index
+    diff = s[:, :500].cpu() != s_ref[:, :500]
+    assert int((diff & ((p_ref[:, :500] - u[:, :500]).abs() > 1e-6)).sum()) == 0
+
+
+def test_cd1_update_c1_shape_vs_oracle(M):
+    """Config C1: one CD-1 update of RBM 10000->1500 at batch 64 against the oracle."""
+    V, H, B = 10000, 1500, 64
+    st, r = oracle_and_gpu(M, V, H, seed=11, lr=0.1, weight_decay=1e-4, momentum=0.5,
+                           final_momentum=0.95, dynamic_lr=True)
+    data = O.synthetic_images(B, V, seed=1234)
+    loss_ref, s = O.cd_train(st, data, 0, 1, RandomField(5, 0))
+    r.set_rng(5, 0)
+    loss = r.train_epoch(data.to(DEV), 0, 1, CD=1)
+    close(loss, loss_ref, dict(rtol=1e-5, atol=1e-7))
+    # a handful of units may legitimately flip inside the 1e-6 band; each flip moves a row/column
+    # of dS by 1/B*lr, so compare robustly: almost all entries tight, none far off
+    dW = (r.W.detach().cpu() - st.W).abs()
+    assert float(dW.max()) < 0.1 / B * 4
+    assert float((dW > 1e-6).float().mean()) < 1e-3
+    close(r.hid_bias, st.hb, dict(rtol=1e-4, atol=2e-5)); close(r.vis_bias, st.vb, dict(rtol=1e-4, atol=2e-5))
+
+
+def test_cd_properties_full_size(M):
+    """Size-independent properties at the C2 shapes (SURVEY 8c known answers)."""
+    V, H, B = 10000, 1500, 64
+    st, r = oracle_and_gpu(M, V, H, seed=2)
+    data = O.synthetic_images(B, V, seed=77).to(DEV)
+    # lr = 0: parameters unchanged, call counter advanced by one
+    r.lr = 0.0
+    W0 = r.W.detach().clone()
+    s0 = r._rng_stream
+    r.train_epoch(data, 0, 1, CD=2)
+    assert torch.equal(r.W.detach(), W0) and r._rng_stream == s0 + 1
+    # B=1, wd=0, mom=0, CD-1: dW = lr (v+ h+^T - v- h-^T)
+    r.lr, r.weight_decay, r.momentum, r.dynamic_lr = 0.5, 0.0, 0.0, False
+    r.W_m.zero_(); r.hb_m.zero_(); r.vb_m.zero_()
+    x = data[:1]
+    r.set_rng(123, 0)
+    from multimodal_idbn_b200 import _lib as L
+    rng = L.RngStruct(123, 0, 0)
+    ph, h0 = r._up(x, sample=True, rng=rng, draw=0)
+    vp, _, vs = r._down(h0, sample=True, rng=rng, draw_u=1, draw_cat=2)
+    hp = r.forward(vs)
+    expect = W0 + 0.5 * (x.t() @ ph - vs.t() @ hp)
+    r.train_epoch(x, 0, 1, CD=1)
+    torch.testing.assert_close(r.W.detach(), expect, rtol=1e-5, atol=1e-6)
+
+
+def test_chain_kernels_vs_oracle_joint_shape(M):
+    """noisy MF (50 steps, mu-pull) and conditional Gibbs (50+1 sweeps) at the joint RBM's shape."""
+    V, H, Dz, K, B = 532, 256, 500, 32, 96
+    st, r = oracle_and_gpu(M, V, H, groups=[(Dz, V)], seed=21, scale=2.0)
+    z = torch.rand(B, Dz, generator=torch.Generator().manual_seed(2))
+    y = O.synthetic_labels(B, K, seed=3)
+    mu = torch.rand(B, Dz, generator=torch.Generator().manual_seed(4))
+    vk = torch.zeros(B, V); km = torch.zeros(B, V); vk[:, Dz:] = y; km[:, Dz:] = 1
+    ref = O.noisy_meanfield(st, vk, km, n_steps=50, mu_pull=(mu, 0.15), fld=RandomField(31, 0))
+    r._mu_pull = {"mu_k": mu.to(DEV), "eta0": 0.15}
+    r.set_rng(31, 0)
+    out = r.noisy_meanfield_annealed(vk.to(DEV), km.to(DEV), n_steps=50)
+    r._mu_pull = None
+    close(out, ref, dict(rtol=2e-4, atol=2e-5))
+    vk = torch.zeros(B, V); km = torch.zeros(B, V); vk[:, :Dz] = z; km[:, :Dz] = 1
+    ref = O.conditional_gibbs(st, vk, km, n_steps=50, fld=RandomField(31, 1))
+    r.set_rng(31, 1)
+    out = r.conditional_gibbs(vk.to(DEV), km.to(DEV), n_steps=50)
+    close(out, ref, dict(rtol=2e-4, atol=2e-5))
+    assert torch.allclose(out[:, Dz:].sum(1).cpu(), torch.ones(B), atol=1e-5)
+
+
+def test_free_energy_best_of_k(M):
+    from multimodal_idbn_b200 import _lib as L
+    V, H, B, K = 532, 256, 33, 7
+    st, r = oracle_and_gpu(M, V, H, groups=[(500, 532)], seed=8, scale=2.0)
+    cand = torch.rand(K, B, V, generator=torch.Generator().manual_seed(9))
+    Fref = torch.stack([O.free_energy(st, c) for c in cand])
+    Fg = torch.stack([M.rbm_free_energy(r, c.to(DEV)) for c in cand])
+    close(Fg, Fref, dict(rtol=1e-5, atol=1e-3))
+    out = torch.empty(B, V, device=DEV); idx = torch.empty(B, dtype=torch.int32, device=DEV)
+    ctx, stm = L.context_for(out)
+    Fc = Fg.contiguous(); cg = cand.to(DEV).contiguous()
+    ctx.check(ctx.lib.imdbn_best_of_k(ctx.handle, L.ptr(cg), L.ptr(Fc), K, B, V, L.ptr(out), L.ptr(idx), stm), "bok")
+    best = Fc.argmin(0)
+    assert torch.equal(idx.long(), best)
+    assert torch.equal(out, cg[best, torch.arange(B, device=DEV)])
+
+
+def test_no_cpu_fallback(M):
+    r = M.RBM(8, 4, 0.1, 1e-4, 0.5).to("cpu")
+    with pytest.raises(RuntimeError):
+        r.forward(torch.zeros(2, 8))
+    with pytest.raises(RuntimeError):
+        r.train_epoch(torch.zeros(2, 8), 0, 1)

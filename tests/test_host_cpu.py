@@ -1,0 +1,172 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol the header declares,
+host logic of the drop-in classes (schedules, pickling, aliases, loud failure without CUDA), and the
+data-parallel statistics exchange over a 2-process gloo group."""
+import ctypes
+import os
+import pickle
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    text = open(os.path.join(REPO, "include", "imdbn_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(imdbn_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_loads_and_exports_header_symbols():
+    from multimodal_idbn_b200.build import build
+    path = build()
+    lib = ctypes.CDLL(path)
+    names = header_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/imdbn_b200.h but not exported"
+    lib.imdbn_abi_version.restype = ctypes.c_int
+    assert lib.imdbn_abi_version() == 1
+    from multimodal_idbn_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == names          # the ctypes table covers the whole header
+
+
+def test_sass_is_sm100a():
+    from multimodal_idbn_b200.build import build
+    out = subprocess.run(["cuobjdump", "-lelf", build()], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_ctx_create_without_gpu_fails_cleanly():
+    if torch.cuda.is_available():
+        pytest.skip("has a GPU")
+    from multimodal_idbn_b200 import _lib
+    lib = _lib.load_library()
+    h = ctypes.c_void_p()
+    assert lib.imdbn_ctx_create(ctypes.byref(h), 0) != 0 and not h.value
+
+
+def test_no_cpu_fallback_and_reference_api_surface(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    import multimodal_idbn_b200 as M
+    r = M.RBM(12, 5, 0.1, 1e-4, 0.5, softmax_groups=[(8, 12)]).to("cpu")
+    for name in ("forward", "_visible_logits", "visible_probs", "sample_visible", "backward",
+                 "backward_sample", "gibbs_step", "train_epoch", "_lin_schedule", "_hot_steps",
+                 "conditional_gibbs_annealed", "noisy_meanfield_annealed", "conditional_gibbs",
+                 "train_epoch_clamped"):
+        assert callable(getattr(r, name))
+    assert list(r.state_dict().keys()) == ["W", "hid_bias", "vis_bias"]
+    assert not hasattr(r, "free_energy")                     # the reference ships without the hook
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        r.forward(torch.zeros(2, 12))
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        r.noisy_meanfield_annealed(torch.zeros(2, 12), torch.zeros(2, 12), n_steps=3)
+    assert r._lin_schedule(0, 50, 3.0, 1.0) == 3.0 and r._lin_schedule(49, 50, 3.0, 1.0) == 1.0
+    assert r._lin_schedule(3, 1, 3.0, 1.0) == 1.0 and r._hot_steps(50, 0.7) == 35
+    p = dict(LEARNING_RATE=0.1, WEIGHT_PENALTY=1e-4, INIT_MOMENTUM=0.5, FINAL_MOMENTUM=0.95,
+             LEARNING_RATE_DYNAMIC=True, SPARSITY=True)
+    d = M.iDBN([20, 10, 6], p, None, None, torch.device("cpu"))
+    assert [l.sparsity for l in d.layers] == [False, True] and d.arch_str == "20-10-6"
+    m = M.iMDBN([20, 10, 6], 4, params=p, device=torch.device("cpu"), num_labels=3)
+    assert m.joint_rbm.num_visible == 9 and m.joint_rbm.softmax_groups == [(6, 9)]
+    m2 = M.iMDBN([20, 10, 6], [5, 5], 4, params=p, device=torch.device("cpu"), num_labels=3,
+                 logging_cfg={"x": 1})
+    assert m2.joint_rbm.num_hidden == 4
+    with pytest.raises(ValueError):
+        M.iMDBN([20, 10], [5, 5], params=p)
+
+
+def test_pickle_layout_and_aliases(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    import multimodal_idbn_b200 as M
+    import imdbn.models as IM
+    import imdbn.models.gdbn_model_complete as MONO
+    assert IM.RBM is M.RBM and MONO.iMDBN is M.iMDBN and M.RBM.__module__ == "imdbn.models.rbm"
+    assert sys.modules["src.classes.rbm_model"].RBM is M.RBM     # legacy Groundeep aliases
+    p = dict(LEARNING_RATE=0.1, WEIGHT_PENALTY=1e-4, INIT_MOMENTUM=0.5, FINAL_MOMENTUM=0.95,
+             LEARNING_RATE_DYNAMIC=True)
+    m = M.iMDBN([20, 10, 6], 4, params=p, device=torch.device("cpu"), num_labels=3)
+    m.z_class_mean = torch.zeros(3, 6)
+    m.save_model(str(tmp_path / "m.pkl"))
+    blob = open(tmp_path / "m.pkl", "rb").read()
+    assert b"imdbn.models.rbm" in blob and b"multimodal_idbn_b200" not in blob
+    d = M.iMDBN.load_model(str(tmp_path / "m.pkl"), device=torch.device("cpu"))
+    assert set(d) >= {"layers", "params", "image_idbn", "joint_rbm", "num_labels", "Dz_img",
+                      "arch_str", "features", "metadata", "z_class_mean"}
+    r = d["joint_rbm"]
+    for k in ("W", "hid_bias", "vis_bias"):
+        assert isinstance(getattr(r, k), torch.nn.Parameter)
+    for k in ("W_m", "hb_m", "vb_m", "num_visible", "num_hidden", "lr", "weight_decay", "momentum",
+              "dynamic_lr", "final_momentum", "sparsity", "sparsity_factor", "softmax_groups"):
+        assert k in r.__dict__
+    assert "_stats_buf" not in r.__dict__
+    # a {"layers": ...} checkpoint feeds load_pretrained_image_idbn
+    m.image_idbn.save_model(str(tmp_path / "i.pkl"))
+    assert m.load_pretrained_image_idbn(str(tmp_path / "i.pkl"))
+    assert not m.load_pretrained_image_idbn(str(tmp_path / "missing.pkl"))
+
+
+WORKER = r"""
+import os, sys, torch, torch.distributed as td
+sys.path.insert(0, {repo!r})
+from oracle import rbm_oracle as O
+from oracle.philox import RandomField
+import multimodal_idbn_b200.dist as D
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+td.init_process_group("gloo", rank=rank, world_size=world)
+D.enable()
+assert D.state().rank == rank and D.state().world == world
+torch.set_num_threads(1)
+V, H, B = 40, 24, 12
+st = O.new_state(V, H, seed=3, groups=[(32, 40)], lr=0.1, weight_decay=1e-4, momentum=0.5,
+                 final_momentum=0.95, dynamic_lr=True, sparsity=True, sparsity_factor=0.1)
+st.W *= 3
+data = torch.cat([O.synthetic_images(B, 32, p=0.4, seed=5), O.synthetic_labels(B, 8, seed=6)], 1)
+full = st.clone()
+loss_full, _ = O.cd_train(full, data, 2, 2, RandomField(9, 4))
+lo, hi = D.shard_rows(B, rank, world)
+s = O.cd_statistics(st, data[lo:hi], 2, RandomField(9, 4), row0=lo)       # global-row addressing
+flat = torch.cat([s["dS"].reshape(-1), s["dh"], s["dv"], s["pos_h_sum"], s["sq_err"].reshape(1)])
+D.state().all_reduce(flat)
+n = V * H
+lr, mom = O.lr_and_momentum(st, 2)
+O.apply_update(st, flat[:n].view(V, H), flat[n:n + H], flat[n + H:n + H + V], B, lr, mom,
+               pos_h_mean=flat[n + H + V:n + 2 * H + V] / B)
+loss = flat[-1] / (B * V)
+for a, b in ((st.W, full.W), (st.hb, full.hb), (st.vb, full.vb), (st.Wm, full.Wm), (loss, loss_full)):
+    torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
+td.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_data_parallel_statistics_two_ranks_gloo(tmp_path):
+    """World size 2 over gloo: shard the minibatch, all-reduce the CD statistics through
+    ``multimodal_idbn_b200.dist``, apply the update -> identical to the single-process update."""
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(repo=REPO))
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port), LOCAL_RANK=str(r), CUDA_VISIBLE_DEVICES="")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=300)
+        assert p.returncode == 0, out
+        assert "ok" in out
+
+
+def test_bench_reference_arm_prints_contract_line():
+    out = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference",
+                          "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    import json
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "samples/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
