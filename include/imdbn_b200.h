@@ -132,6 +132,11 @@ int64_t imdbn_stats_size(const imdbn_rbm* rbm);
 int imdbn_apply_update(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* stats,
                        const imdbn_update* upd, float* loss_out, imdbn_stream stream);
 
+/* The association statistics alone (rbm.py:200,209): dS_out [V,H] = vp^T hp - vn^T hn with
+ * vp, vn [B,V] and hp, hn [B,H]. */
+int imdbn_assoc_stats(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* vp, const float* hp,
+                      const float* vn, const float* hn, int B, float* dS_out, imdbn_stream stream);
+
 /* ---- conditional inference chains ---------------------------------------------------------- */
 enum { IMDBN_CHAIN_NOISY_MF = 0, IMDBN_CHAIN_COND_GIBBS = 1 };
 

@@ -80,6 +80,7 @@ SIGNATURES = {
     "imdbn_cd_stats": (_I, [_P, C.POINTER(RbmStruct), _P, _I, _I, C.POINTER(RngStruct), _P, _P]),
     "imdbn_stats_size": (C.c_int64, [C.POINTER(RbmStruct)]),
     "imdbn_apply_update": (_I, [_P, C.POINTER(RbmStruct), _P, C.POINTER(UpdateStruct), _P, _P]),
+    "imdbn_assoc_stats": (_I, [_P, C.POINTER(RbmStruct), _P, _P, _P, _P, _I, _P, _P]),
     "imdbn_run_chain": (_I, [_P, C.POINTER(RbmStruct), C.POINTER(ChainStruct), _I, _P, _P,
                              C.POINTER(RngStruct), _P]),
     "imdbn_cd_train_clamped": (_I, [_P, C.POINTER(RbmStruct), _P, _P, _I, C.POINTER(ClampedCfgStruct),

@@ -139,6 +139,20 @@ inline Groups make_groups(const imdbn_rbm* r) {
     return g;
 }
 
+// Stream-K partition of the tensor-core passes (tc_gemm.cu): the flattened (output tile, k-iteration)
+// space of `total` iterations is cut into G contiguous, equally long ranges, one per CTA.  An output
+// tile therefore receives partial sums from a few consecutive CTAs ("slabs"), which the finish
+// kernels add in CTA order.  k_iters == 0 means "not stream-K": a uniform number of K splits.
+struct SKPlan { int k_iters, q, r, tile_w; };
+__host__ __device__ inline int sk_beg(const SKPlan& p, int c) { return c * p.q + (c < p.r ? c : p.r); }
+__host__ __device__ inline int sk_cta_of(const SKPlan& p, int idx) {
+    const int big = p.r * (p.q + 1);
+    return idx < big ? idx / (p.q + 1) : p.r + (idx - big) / p.q;
+}
+__host__ __device__ inline int sk_nslabs(const SKPlan& p, int tile) {
+    return sk_cta_of(p, (tile + 1) * p.k_iters - 1) - sk_cta_of(p, tile * p.k_iters) + 1;
+}
+
 // exact (never FMA-contracted) forms of the reference's element-wise expressions
 __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }

@@ -26,18 +26,29 @@ inline int ew_blocks(size_t n, int num_sms) {
 }
 
 struct PassPlan {
-    int splits;
+    int splits;          // uniform K splits (FFMA engine) or max slabs per tile (stream-K tensor-core pass)
     int kps;
+    SKPlan sk;           // sk.k_iters != 0 -> tensor-core stream-K pass
     size_t part_floats;
 };
 
-PassPlan plan_pass(const imdbn_ctx* ctx, int M, int N, int K) {
-    PassPlan p;
-    p.splits = choose_splits(M, N, K, ctx->num_sms);
-    int kps = (K + p.splits - 1) / p.splits;
-    kps = (kps + GBK - 1) / GBK * GBK;
-    p.kps = kps;
-    p.splits = (K + kps - 1) / kps;
+// plan of the up pass (up = true: [B,V] x [V,H]) or the down pass ([B,H] x [H,V])
+PassPlan plan_pass(const imdbn_ctx* ctx, const imdbn_rbm* r, int B, bool up) {
+    const int M = B, N = up ? r->H : r->V, K = up ? r->V : r->H;
+    PassPlan p{};
+    const bool tc = ctx->precision == IMDBN_PREC_TF32 &&
+                    (up ? tc_up_supported(ctx, r, B) : tc_down_supported(ctx, r, B));
+    if (tc) {
+        p.sk = tc_plan(ctx, N, K);
+        p.splits = tc_plan_max_slabs(p.sk, N);
+        p.kps = 0;
+    } else {
+        p.splits = choose_splits(M, N, K, ctx->num_sms);
+        int kps = (K + p.splits - 1) / p.splits;
+        kps = (kps + GBK - 1) / GBK * GBK;
+        p.kps = kps;
+        p.splits = (K + kps - 1) / kps;
+    }
     p.part_floats = (size_t)p.splits * M * N;
     return p;
 }
@@ -46,8 +57,7 @@ PassPlan plan_pass(const imdbn_ctx* ctx, int M, int N, int K) {
 int gemm_up(imdbn_ctx* ctx, const imdbn_rbm* r, const float* v, int B, const PassPlan& pl,
             float* part, cudaStream_t st) {
     ProfScope prof(ctx, IMDBN_KERNEL_UP, r->V, r->H, st);
-    if (ctx->precision == IMDBN_PREC_TF32 && tc_up_supported(ctx, r, B))
-        return tc_gemm_up(ctx, r, v, B, part, st);
+    if (pl.sk.k_iters) return tc_gemm_up(ctx, r, v, B, part, st);
     GemmArgs g{};
     g.A = v; g.sAm = r->V; g.sAk = 1;
     g.B = r->W; g.sBk = r->H; g.sBn = 1;
@@ -63,8 +73,7 @@ int gemm_up(imdbn_ctx* ctx, const imdbn_rbm* r, const float* v, int B, const Pas
 int gemm_down(imdbn_ctx* ctx, const imdbn_rbm* r, const float* h, int B, const PassPlan& pl,
               float* part, cudaStream_t st) {
     ProfScope prof(ctx, IMDBN_KERNEL_DOWN, r->V, r->H, st);
-    if (ctx->precision == IMDBN_PREC_TF32 && tc_down_supported(ctx, r, B))
-        return tc_gemm_down(ctx, r, h, B, part, st);
+    if (pl.sk.k_iters) return tc_gemm_down(ctx, r, h, B, part, st);
     GemmArgs g{};
     g.A = h; g.sAm = r->H; g.sAk = 1;
     g.B = r->W; g.sBk = 1; g.sBn = r->H;
@@ -109,7 +118,7 @@ int up_pass(imdbn_ctx* ctx, const imdbn_rbm* r, const float* v, int B, float T, 
     int rc = gemm_up(ctx, r, v, B, pl, part, st);
     if (rc) return rc;
     k_finish_up<<<ew_blocks((size_t)B * r->H, ctx->num_sms), 256, 0, st>>>(
-        part, pl.splits, B, r->H, r->hb, fmaxf(1e-6f, T), p_out, s_out, key, draw_u);
+        part, pl.splits, pl.sk, B, r->H, r->hb, fmaxf(1e-6f, T), p_out, s_out, key, draw_u);
     IMDBN_CHECK_LAUNCH(ctx, "k_finish_up");
     return 0;
 }
@@ -123,7 +132,7 @@ int down_pass(imdbn_ctx* ctx, const imdbn_rbm* r, const float* h, int B, float T
     const Groups gr = make_groups(r);
     float* lg = logits_out ? logits_out : (gr.n ? logits_tmp : nullptr);
     k_finish_down<<<ew_blocks((size_t)B * r->V, ctx->num_sms), 256, 0, st>>>(
-        part, pl.splits, B, r->V, r->vb, fmaxf(1e-6f, T), p_out, lg, s_out, key, draw_u);
+        part, pl.splits, pl.sk, B, r->V, r->vb, fmaxf(1e-6f, T), p_out, lg, s_out, key, draw_u);
     IMDBN_CHECK_LAUNCH(ctx, "k_finish_down");
     if (gr.n && (p_out || s_out)) {
         // the groups need a probability buffer even when the caller only wants samples
@@ -241,7 +250,7 @@ int cd_core(imdbn_ctx* ctx, const imdbn_rbm* r, const float* data, int B, int k,
     if (rc) return rc;
     IMDBN_ARG(ctx, data && B > 0 && k >= 1 && rng);
     const int V = r->V, H = r->H;
-    const PassPlan pu = plan_pass(ctx, B, H, V), pd = plan_pass(ctx, B, V, H);
+    const PassPlan pu = plan_pass(ctx, r, B, true), pd = plan_pass(ctx, r, B, false);
     const size_t nBH = (size_t)B * H, nBV = (size_t)B * V;
     const int nb_sq = (std::max(V, H) + 255) / 256;
     size_t bytes = pad256(std::max(pu.part_floats, pd.part_floats)) + 3 * pad256(nBH) +
@@ -290,7 +299,7 @@ int clamped_core(imdbn_ctx* ctx, const imdbn_rbm* r, const float* v_known, const
     const int V = r->V, H = r->H;
     const int n = cfg->use_noisy_init ? std::max(10, cfg->cond_init_steps) : cfg->cond_init_steps;
     IMDBN_ARG(ctx, n >= 0 && n <= CHAIN_MAX_STEPS);
-    const PassPlan pu = plan_pass(ctx, B, H, V), pd = plan_pass(ctx, B, V, H);
+    const PassPlan pu = plan_pass(ctx, r, B, true), pd = plan_pass(ctx, r, B, false);
     const size_t nBH = (size_t)B * H, nBV = (size_t)B * V;
     const int nb_sq = (std::max(V, H) + 255) / 256;
     size_t bytes = pad256(std::max(pu.part_floats, pd.part_floats)) + 3 * pad256(nBH) +
@@ -466,7 +475,7 @@ int imdbn_up(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* v, int B, float 
     int rc = check_rbm(ctx, rbm, false);
     if (rc) return rc;
     IMDBN_ARG(ctx, v && B > 0 && (p_out || s_out) && (!s_out || rng));
-    const PassPlan pu = plan_pass(ctx, B, rbm->H, rbm->V);
+    const PassPlan pu = plan_pass(ctx, rbm, B, true);
     rc = arena_begin(ctx, pad256(pu.part_floats) + tc_ws_bytes(ctx, rbm, B), st);
     if (rc) return rc;
     float* part = arena_take<float>(ctx, pu.part_floats);
@@ -482,7 +491,7 @@ int imdbn_down(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* h, int B, floa
     int rc = check_rbm(ctx, rbm, false);
     if (rc) return rc;
     IMDBN_ARG(ctx, h && B > 0 && (p_out || s_out || logits_out) && (!s_out || rng));
-    const PassPlan pd = plan_pass(ctx, B, rbm->V, rbm->H);
+    const PassPlan pd = plan_pass(ctx, rbm, B, false);
     const size_t nBV = (size_t)B * rbm->V;
     rc = arena_begin(ctx, pad256(pd.part_floats) + pad256(2 * nBV) + tc_ws_bytes(ctx, rbm, B), st);
     if (rc) return rc;
@@ -524,13 +533,13 @@ int imdbn_free_energy(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* v, int 
     int rc = check_rbm(ctx, rbm, false);
     if (rc) return rc;
     IMDBN_ARG(ctx, v && F_out && B > 0);
-    const PassPlan pu = plan_pass(ctx, B, rbm->H, rbm->V);
+    const PassPlan pu = plan_pass(ctx, rbm, B, true);
     rc = arena_begin(ctx, pad256(pu.part_floats) + tc_ws_bytes(ctx, rbm, B), st);
     if (rc) return rc;
     float* part = arena_take<float>(ctx, pu.part_floats);
     rc = gemm_up(ctx, rbm, v, B, pu, part, st);
     if (rc) return rc;
-    k_free_energy<<<B, 256, 0, st>>>(part, pu.splits, v, B, rbm->V, rbm->H, rbm->hb, rbm->vb, F_out);
+    k_free_energy<<<B, 256, 0, st>>>(part, pu.splits, pu.sk, v, B, rbm->V, rbm->H, rbm->hb, rbm->vb, F_out);
     IMDBN_CHECK_LAUNCH(ctx, "k_free_energy");
     return 0;
 }
@@ -564,6 +573,14 @@ int imdbn_apply_update(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* stats,
                                                                (float)upd->batch_global);
     IMDBN_CHECK_LAUNCH(ctx, "k_weight_update");
     return bias_update(ctx, rbm, stats + n, upd, (float)upd->batch_global * rbm->V, loss_out, st);
+}
+
+int imdbn_assoc_stats(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* vp, const float* hp,
+                      const float* vn, const float* hn, int B, float* dS_out, imdbn_stream stream) {
+    int rc = check_rbm(ctx, rbm, false);
+    if (rc) return rc;
+    IMDBN_ARG(ctx, vp && hp && vn && hn && dS_out && B > 0);
+    return gemm_stats(ctx, rbm, vp, hp, vn, hn, B, dS_out, nullptr, (cudaStream_t)stream);
 }
 
 int imdbn_run_chain(imdbn_ctx* ctx, const imdbn_rbm* rbm, const imdbn_chain* ch, int B,

@@ -7,15 +7,16 @@
 namespace imdbn {
 
 // ---- up pass finish: p = sigmoid((sum_s part + hb)/T), s = (p > U)           rbm.py:92,175,203
-__global__ void k_finish_up(const float* __restrict__ part, int splits, int B, int H,
+__global__ void k_finish_up(const float* __restrict__ part, int splits, SKPlan sk, int B, int H,
                             const float* __restrict__ hb, float T, float* __restrict__ p_out,
                             float* __restrict__ s_out, RngKey key, uint32_t draw_u) {
     const size_t n = (size_t)B * H;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
          i += (size_t)gridDim.x * blockDim.x) {
         const int b = (int)(i / H), j = (int)(i % H);
+        const int ns = sk.k_iters ? sk_nslabs(sk, j / sk.tile_w) : splits;
         float x = 0.0f;
-        for (int s = 0; s < splits; ++s) x += part[(size_t)s * n + i];
+        for (int s = 0; s < ns; ++s) x += part[(size_t)s * n + i];
         x = add_rn(x, hb[j]) / T;
         const float p = sigmoidf_ref(x);
         if (p_out) p_out[i] = p;
@@ -25,7 +26,7 @@ __global__ void k_finish_up(const float* __restrict__ part, int splits, int B, i
 
 // ---- down pass finish: logits = (sum_s part + vb)/T, p = sigmoid(logits), s = (p > U)
 //      (softmax groups are overwritten afterwards by k_groups)                 rbm.py:96,110,125
-__global__ void k_finish_down(const float* __restrict__ part, int splits, int B, int V,
+__global__ void k_finish_down(const float* __restrict__ part, int splits, SKPlan sk, int B, int V,
                               const float* __restrict__ vb, float T, float* __restrict__ p_out,
                               float* __restrict__ logits_out, float* __restrict__ s_out,
                               RngKey key, uint32_t draw_u) {
@@ -33,8 +34,9 @@ __global__ void k_finish_down(const float* __restrict__ part, int splits, int B,
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
          i += (size_t)gridDim.x * blockDim.x) {
         const int b = (int)(i / V), c = (int)(i % V);
+        const int ns = sk.k_iters ? sk_nslabs(sk, c / sk.tile_w) : splits;
         float x = 0.0f;
-        for (int s = 0; s < splits; ++s) x += part[(size_t)s * n + i];
+        for (int s = 0; s < ns; ++s) x += part[(size_t)s * n + i];
         x = add_rn(x, vb[c]) / T;
         if (logits_out) logits_out[i] = x;
         const float p = sigmoidf_ref(x);
@@ -185,15 +187,16 @@ __global__ void k_clampmix(const float* __restrict__ a, const float* __restrict_
 }
 
 // ---- free energy finish (energy_utils.py:25-28): F[b] = -v.b_v - sum_j softplus(pre_j)
-__global__ void k_free_energy(const float* __restrict__ part, int splits, const float* __restrict__ v,
+__global__ void k_free_energy(const float* __restrict__ part, int splits, SKPlan sk, const float* __restrict__ v,
                               int B, int V, int H, const float* __restrict__ hb,
                               const float* __restrict__ vb, float* __restrict__ F) {
     const int b = blockIdx.x;
     const size_t n = (size_t)B * H;
     float th = 0.0f, tv = 0.0f;
     for (int j = threadIdx.x; j < H; j += blockDim.x) {
+        const int ns = sk.k_iters ? sk_nslabs(sk, j / sk.tile_w) : splits;
         float x = 0.0f;
-        for (int s = 0; s < splits; ++s) x += part[(size_t)s * n + (size_t)b * H + j];
+        for (int s = 0; s < ns; ++s) x += part[(size_t)s * n + (size_t)b * H + j];
         x = add_rn(x, hb[j]);
         th += (x > 20.0f) ? x : log1pf(expf(x));   // torch softplus, threshold 20
     }

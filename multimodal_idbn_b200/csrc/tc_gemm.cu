@@ -1,14 +1,548 @@
-// Tensor-core (tcgen05 / TMEM / TMA) path -- placeholder until the kernels land: reports
-// "unsupported" so every pass runs on the fp32 FFMA engine.
+// Tensor-core path (sm_100a): tcgen05.mma kind::tf32 with fp32 accumulators in TMEM, operands fed
+// by TMA straight from the fp32 master tensors (no shadow copies), warp-specialised
+// producer / MMA-issuer / epilogue roles synchronised with mbarriers.
+//
+//  k_tc_stream<A_MN>  the weight-streaming passes at small batch (HBM-bound):
+//        up   (rbm.py:92)  D[h, b] = sum_v W[v,h] a[b,v]   A = W tile, MN-major (h contiguous)
+//        down (rbm.py:96)  D[v, b] = sum_h W[v,h] a[b,h]   A = W tile, K-major
+//     "swap-AB": the 128-row MMA M dimension is the OUTPUT FEATURE, the batch (<= 256) is N, so a
+//     batch of 64 uses the full datapath.  Work is stream-K partitioned (SKPlan): every CTA streams
+//     an equal, contiguous share of W exactly once; per-tile partial sums go to slabs that the finish
+//     kernels (bias / sigmoid / Philox sampling) add in a fixed order.
+//
+//  k_tc_stats<UPDATE> CD statistics + update (rbm.py:200,209,212-213):
+//        dS[v,h] = sum_b vp[b,v] hp[b,h] - sum_b vn[b,v] hn[b,h]   (both operands MN-major; the
+//        negative phase uses the a_negate bit of the instruction descriptor), 128x128 tiles,
+//        double-buffered TMEM accumulators; the epilogue stages the tile through shared memory and
+//        streams W / W_m with coalesced accesses:  W_m <- mom W_m + lr(dS/B - wd W);  W <- W + W_m.
+#include <cuda.h>
+
+#include <unordered_map>
+
 #include "tc_gemm.cuh"
+#include "tc_ptx.cuh"
 
 namespace imdbn {
-bool tc_up_supported(const imdbn_ctx*, const imdbn_rbm*, int) { return false; }
-bool tc_down_supported(const imdbn_ctx*, const imdbn_rbm*, int) { return false; }
-bool tc_stats_supported(const imdbn_ctx*, const imdbn_rbm*, int) { return false; }
+
+using namespace ptx;
+
+// ------------------------------------------------------------------------------------------------
+// host state: driver entry point + tensor-map cache
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+struct MapKey {
+    const void* ptr; int inner, outer, box_inner, box_outer;   // box_inner: 32 = SW128, -32 = SW128 with 32B atoms
+    bool operator==(const MapKey& o) const {
+        return ptr == o.ptr && inner == o.inner && outer == o.outer && box_inner == o.box_inner &&
+               box_outer == o.box_outer;
+    }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        size_t h = std::hash<const void*>()(k.ptr);
+        h = h * 1000003u ^ (size_t)k.inner; h = h * 1000003u ^ (size_t)k.outer;
+        h = h * 1000003u ^ (size_t)k.box_inner; h = h * 1000003u ^ (size_t)k.box_outer;
+        return h;
+    }
+};
+
+struct TcState {
+    EncodeTiledFn encode = nullptr;
+    bool attrs_set = false;
+    std::unordered_map<MapKey, CUtensorMap, MapKeyHash> maps;
+};
+
+static TcState* tc_state(imdbn_ctx* ctx) {
+    if (!ctx->tc) {
+        TcState* s = new TcState();
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            s->encode = (EncodeTiledFn)fn;
+        ctx->tc = s;
+    }
+    return static_cast<TcState*>(ctx->tc);
+}
+
+void tc_destroy(imdbn_ctx* ctx) {
+    delete static_cast<TcState*>(ctx->tc);
+    ctx->tc = nullptr;
+}
+
+// 2-D fp32 row-major [outer, inner] tensor, box [box_outer, box_inner = 32 floats = 128 B], SW128.
+// atom32 selects CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (for MN-major tf32 operands).
+static const CUtensorMap* get_map(imdbn_ctx* ctx, const float* ptr, int inner, int outer, int box_outer,
+                                  bool atom32) {
+    TcState* s = tc_state(ctx);
+    MapKey k{ptr, inner, outer, atom32 ? -32 : 32, box_outer};
+    auto it = s->maps.find(k);
+    if (it != s->maps.end()) return &it->second;
+    if (s->maps.size() > 4096) s->maps.clear();
+    CUtensorMap m;
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t strides[1] = {(cuuint64_t)inner * sizeof(float)};
+    cuuint32_t box[2] = {32u, (cuuint32_t)box_outer};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = s->encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return nullptr;
+    return &s->maps.emplace(k, m).first->second;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight-streaming pass kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int TS_BM = 128;                 // output features per tile (MMA M)
+constexpr int TS_BK = 64;                  // reduction elements per pipeline stage
+constexpr int TS_STAGES = 4;                // maximum; fewer when the batch tile is wide (StreamArgs::stages)
+constexpr int TS_THREADS = 192;            // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int TS_A_BYTES = TS_BM * TS_BK * 4;
+
+struct StreamArgs {
+    int M_total, K_total, B, Npad;
+    SKPlan sk;
+    int total_iters;
+    float* part;                           // [slab][B][M_total]
+    uint32_t tmem_cols;
+    int stages;
+};
+
+__host__ __device__ inline int ts_stage_bytes(int Npad) { return TS_A_BYTES + Npad * TS_BK * 4; }
+
+template <bool A_MN>
+__global__ void __launch_bounds__(TS_THREADS, 1)
+k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, StreamArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int stage_bytes = ts_stage_bytes(a.Npad);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.stages * stage_bytes);
+    uint64_t* full = bars;                      // [TS_STAGES]
+    uint64_t* empty = bars + TS_STAGES;         // [TS_STAGES]
+    uint64_t* acc_full = bars + 2 * TS_STAGES;  // [2]
+    uint64_t* acc_empty = acc_full + 2;         // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cta = blockIdx.x;
+    const int beg = sk_beg(a.sk, cta), end = sk_beg(a.sk, cta + 1);
+    const int k_iters = a.sk.k_iters;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, a.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int it = beg; it < end; ++it) {
+                const int tile = it / k_iters, kit = it - tile * k_iters;
+                const int m0 = tile * TS_BM, k0 = kit * TS_BK;
+                uint8_t* sA = smem + stage * stage_bytes;
+                uint8_t* sB = sA + TS_A_BYTES;
+                mbar_wait(&empty[stage], phase ^ 1);
+                mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
+                if (A_MN) {          // W[k rows, 32 features] boxes: one per 32-feature column block
+#pragma unroll
+                    for (int cb = 0; cb < TS_BM / 32; ++cb)
+                        tma_load_2d(sA + cb * (TS_BK * 128), &tmA, m0 + cb * 32, k0, &full[stage]);
+                } else {             // W[128 feature rows, 32 k] boxes: one per 32-wide k block
+#pragma unroll
+                    for (int j = 0; j < TS_BK / 32; ++j)
+                        tma_load_2d(sA + j * (TS_BM * 128), &tmA, k0 + j * 32, m0, &full[stage]);
+                }
+#pragma unroll
+                for (int j = 0; j < TS_BK / 32; ++j)
+                    tma_load_2d(sB + j * (a.Npad * 128), &tmB, k0 + j * 32, 0, &full[stage]);
+                if (++stage == a.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (elect_one()) {
+            const uint32_t idesc = idesc_tf32(TS_BM, a.Npad, A_MN, false, false);
+            int stage = 0; uint32_t phase = 0;
+            int seg = 0;
+            for (int cur = beg; cur < end; ++seg) {
+                const int tile = cur / k_iters, kit0 = cur - tile * k_iters;
+                const int n_it = min(end - cur, k_iters - kit0);
+                const int buf = seg & 1;
+                mbar_wait(&acc_empty[buf], ((seg >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * a.Npad);
+                for (int i = 0; i < n_it; ++i) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sA = smem_u32(smem + stage * stage_bytes);
+                    const uint32_t sB = sA + TS_A_BYTES;
+#pragma unroll
+                    for (int g = 0; g < TS_BK / 8; ++g) {       // one MMA per 8 k (tf32 UMMA_K)
+                        uint64_t ad, bd;
+                        if (A_MN)   // k-group g = rows 8g..8g+7 (two 4-row swizzle atoms) of every column-block box
+                            ad = smem_desc(sA + g * 1024, TS_BK * 128, 512, LAYOUT_SW128_BASE32B);
+                        else        // K-major: 32-wide k block g/4, 32-byte step inside the swizzle row
+                            ad = smem_desc(sA + (g / 4) * (TS_BM * 128) + (g % 4) * 32, 16, 1024, LAYOUT_SW128);
+                        bd = smem_desc(sB + (g / 4) * (a.Npad * 128) + (g % 4) * 32, 16, 1024, LAYOUT_SW128);
+                        mma_tf32(d_tmem, ad, bd, idesc, (i | g) != 0);
+                    }
+                    mma_commit(&empty[stage]);                  // smem slot free when these MMAs retire
+                    if (++stage == a.stages) { stage = 0; phase ^= 1; }
+                }
+                mma_commit(&acc_full[buf]);
+                cur += n_it;
+            }
+        }
+    } else {
+        // ===================== epilogue: TMEM -> partial slab =====================
+        const int quad = warp & 3;                               // TMEM lane quadrant this warp may read
+        int seg = 0;
+        for (int cur = beg; cur < end; ++seg) {
+            const int tile = cur / k_iters, kit0 = cur - tile * k_iters;
+            const int n_it = min(end - cur, k_iters - kit0);
+            const int buf = seg & 1;
+            const int slab = cta - sk_cta_of(a.sk, tile * k_iters);
+            mbar_wait(&acc_full[buf], (seg >> 1) & 1);
+            tc_fence_after();
+            const int m = tile * TS_BM + quad * 32 + lane;
+            float* dst = a.part + (size_t)slab * a.B * a.M_total + m;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * a.Npad);
+            for (int c0 = 0; c0 < a.Npad; c0 += 16) {
+                float v[16];
+                tmem_ld16(taddr + c0, v);
+                if (m < a.M_total) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (c0 + i < a.B) dst[(size_t)(c0 + i) * a.M_total] = v[i];
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            cur += n_it;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, a.tmem_cols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CD statistics + update kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int ST_BM = 128;                 // visible units per tile (MMA M)
+constexpr int ST_BN = 128;                 // hidden units per tile  (MMA N)
+constexpr int ST_KC = 32;                  // batch rows per pipeline stage and segment
+constexpr int ST_STAGES = 2;
+constexpr int ST_EPI_WARPS = 8;
+constexpr int ST_THREADS = 64 + ST_EPI_WARPS * 32;
+constexpr int ST_SEG_A = ST_BM * ST_KC * 4;          // 16 KB: 4 boxes [32 rows x 128 B]
+constexpr int ST_SEG_B = ST_BN * ST_KC * 4;          // 16 KB
+constexpr int ST_STAGE_BYTES = 2 * (ST_SEG_A + ST_SEG_B);   // positive + negative phase
+constexpr int ST_STG_LD = 65;                        // staging row stride (floats), 64 columns per warp
+constexpr int ST_STG_BYTES = ST_EPI_WARPS * 32 * ST_STG_LD * 4;
+
+struct StatsArgs {
+    int V, H, B;
+    int m_tiles, n_tiles, k_chunks;
+    float* W; float* Wm; float* dS;
+    float lr, mom, wd, bsz;
+};
+
+template <bool UPDATE>
+__global__ void __launch_bounds__(ST_THREADS, 1)
+k_tc_stats(const __grid_constant__ CUtensorMap tmVP, const __grid_constant__ CUtensorMap tmVN,
+           const __grid_constant__ CUtensorMap tmHP, const __grid_constant__ CUtensorMap tmHN, StatsArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float* staging = reinterpret_cast<float*>(smem + ST_STAGES * ST_STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ST_STAGES * ST_STAGE_BYTES + ST_STG_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + ST_STAGES;
+    uint64_t* acc_full = bars + 2 * ST_STAGES;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles_total = a.m_tiles * a.n_tiles;
+    // contiguous, balanced tile ranges (consecutive tiles share the visible block -> L2-friendly)
+    const int q = n_tiles_total / gridDim.x, r = n_tiles_total % gridDim.x;
+    const int t_beg = blockIdx.x * q + min((int)blockIdx.x, r);
+    const int t_end = t_beg + q + ((int)blockIdx.x < r ? 1 : 0);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmVP); tma_prefetch_desc(&tmVN); tma_prefetch_desc(&tmHP); tma_prefetch_desc(&tmHN);
+        for (int s = 0; s < ST_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], ST_EPI_WARPS); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * ST_BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = t_beg; t < t_end; ++t) {
+                const int m0 = (t / a.n_tiles) * ST_BM, n0 = (t % a.n_tiles) * ST_BN;
+                for (int kc = 0; kc < a.k_chunks; ++kc) {
+                    const int b0 = kc * ST_KC;
+                    uint8_t* s0 = smem + stage * ST_STAGE_BYTES;
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full[stage], ST_STAGE_BYTES);
+#pragma unroll
+                    for (int cb = 0; cb < ST_BM / 32; ++cb) {
+                        tma_load_2d(s0 + cb * 4096, &tmVP, m0 + cb * 32, b0, &full[stage]);
+                        tma_load_2d(s0 + ST_SEG_A + cb * 4096, &tmVN, m0 + cb * 32, b0, &full[stage]);
+                    }
+#pragma unroll
+                    for (int cb = 0; cb < ST_BN / 32; ++cb) {
+                        tma_load_2d(s0 + 2 * ST_SEG_A + cb * 4096, &tmHP, n0 + cb * 32, b0, &full[stage]);
+                        tma_load_2d(s0 + 2 * ST_SEG_A + ST_SEG_B + cb * 4096, &tmHN, n0 + cb * 32, b0, &full[stage]);
+                    }
+                    if (++stage == ST_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            const uint32_t id_pos = idesc_tf32(ST_BM, ST_BN, true, true, false);
+            const uint32_t id_neg = idesc_tf32(ST_BM, ST_BN, true, true, true);     // -A * B
+            int stage = 0; uint32_t phase = 0;
+            int seg = 0;
+            for (int t = t_beg; t < t_end; ++t, ++seg) {
+                const int buf = seg & 1;
+                mbar_wait(&acc_empty[buf], ((seg >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ST_BN);
+                for (int kc = 0; kc < a.k_chunks; ++kc) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t s0 = smem_u32(smem + stage * ST_STAGE_BYTES);
+#pragma unroll
+                    for (int g = 0; g < ST_KC / 8; ++g) {
+                        const uint64_t ap = smem_desc(s0 + g * 1024, 4096, 512, LAYOUT_SW128_BASE32B);
+                        const uint64_t an = smem_desc(s0 + ST_SEG_A + g * 1024, 4096, 512, LAYOUT_SW128_BASE32B);
+                        const uint64_t bp = smem_desc(s0 + 2 * ST_SEG_A + g * 1024, 4096, 512, LAYOUT_SW128_BASE32B);
+                        const uint64_t bn = smem_desc(s0 + 2 * ST_SEG_A + ST_SEG_B + g * 1024, 4096, 512,
+                                                      LAYOUT_SW128_BASE32B);
+                        mma_tf32(d_tmem, ap, bp, id_pos, (kc | g) != 0);
+                        mma_tf32(d_tmem, an, bn, id_neg, 1u);
+                    }
+                    mma_commit(&empty[stage]);
+                    if (++stage == ST_STAGES) { stage = 0; phase ^= 1; }
+                }
+                mma_commit(&acc_full[buf]);
+            }
+        }
+    } else {
+        // ===================== epilogue =====================
+        const int e = warp - 2;                       // 0..7
+        const int quad = warp & 3;                    // TMEM lane quadrant
+        const int half = e >> 2;                      // which 64-column half of the tile
+        float* stg = staging + e * 32 * ST_STG_LD;
+        int seg = 0;
+        for (int t = t_beg; t < t_end; ++t, ++seg) {
+            const int buf = seg & 1;
+            const int m0 = (t / a.n_tiles) * ST_BM + quad * 32;
+            const int n0 = (t % a.n_tiles) * ST_BN + half * 64;
+            mbar_wait(&acc_full[buf], (seg >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * ST_BN + half * 64);
+#pragma unroll
+            for (int c0 = 0; c0 < 64; c0 += 16) {
+                float v[16];
+                tmem_ld16(taddr + c0, v);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) stg[lane * ST_STG_LD + c0 + i] = v[i];
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);   // accumulator drained: MMA may reuse it
+
+            // rows of this warp's 32 x 64 sub-tile, lanes along the hidden (contiguous) dimension
+            const int h_a = n0 + lane, h_b = n0 + 32 + lane;
+            const bool ok_a = h_a < a.H, ok_b = h_b < a.H;
+#pragma unroll 1
+            for (int r0 = 0; r0 < 32; r0 += 8) {
+                float w[8][2], wm[8][2];
+                if (UPDATE) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = m0 + r0 + i;
+                        const size_t o = (size_t)row * a.H;
+                        const bool rok = row < a.V;
+                        w[i][0] = (rok && ok_a) ? a.W[o + h_a] : 0.f;
+                        w[i][1] = (rok && ok_b) ? a.W[o + h_b] : 0.f;
+                        wm[i][0] = (rok && ok_a) ? a.Wm[o + h_a] : 0.f;
+                        wm[i][1] = (rok && ok_b) ? a.Wm[o + h_b] : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = m0 + r0 + i;
+                    if (row >= a.V) continue;
+                    const size_t o = (size_t)row * a.H;
+                    const float s_a = stg[(r0 + i) * ST_STG_LD + lane];
+                    const float s_b = stg[(r0 + i) * ST_STG_LD + 32 + lane];
+                    if (UPDATE) {
+                        // W_m <- mom*W_m + lr*((S+ - S-)/bsz - wd*W);  W <- W + W_m   (rbm.py:212-213)
+                        if (ok_a) {
+                            const float g = add_rn(s_a / a.bsz, -mul_rn(a.wd, w[i][0]));
+                            const float m = add_rn(mul_rn(wm[i][0], a.mom), mul_rn(a.lr, g));
+                            a.Wm[o + h_a] = m; a.W[o + h_a] = add_rn(w[i][0], m);
+                        }
+                        if (ok_b) {
+                            const float g = add_rn(s_b / a.bsz, -mul_rn(a.wd, w[i][1]));
+                            const float m = add_rn(mul_rn(wm[i][1], a.mom), mul_rn(a.lr, g));
+                            a.Wm[o + h_b] = m; a.W[o + h_b] = add_rn(w[i][1], m);
+                        }
+                    } else {
+                        if (ok_a) a.dS[o + h_a] = s_a;
+                        if (ok_b) a.dS[o + h_b] = s_b;
+                    }
+                }
+            }
+            __syncwarp();     // staging is rewritten by the next tile
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 2 * ST_BN);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static inline int npad_of(int B) { return std::max(16, (B + 15) / 16 * 16); }
+static inline uint32_t pow2_cols(int n) { uint32_t c = 32; while ((int)c < n) c <<= 1; return c; }
+
+bool tc_shape_ok(const imdbn_rbm* r, int B) {
+    return r->V % 4 == 0 && r->H % 4 == 0 && aligned16(r->W) && B >= 1;
+}
+
+bool tc_up_supported(const imdbn_ctx* ctx, const imdbn_rbm* r, int B) {
+    return tc_shape_ok(r, B) && B <= 256 && tc_state(const_cast<imdbn_ctx*>(ctx))->encode != nullptr;
+}
+bool tc_down_supported(const imdbn_ctx* ctx, const imdbn_rbm* r, int B) { return tc_up_supported(ctx, r, B); }
+bool tc_stats_supported(const imdbn_ctx* ctx, const imdbn_rbm* r, int B) {
+    return tc_shape_ok(r, B) && tc_state(const_cast<imdbn_ctx*>(ctx))->encode != nullptr;
+}
 size_t tc_ws_bytes(const imdbn_ctx*, const imdbn_rbm*, int) { return 0; }
-int tc_gemm_up(imdbn_ctx* ctx, const imdbn_rbm*, const float*, int, float*, cudaStream_t) { return fail(ctx, -4, "tc path not built"); }
-int tc_gemm_down(imdbn_ctx* ctx, const imdbn_rbm*, const float*, int, float*, cudaStream_t) { return fail(ctx, -4, "tc path not built"); }
-int tc_gemm_stats(imdbn_ctx* ctx, const imdbn_rbm*, const float*, const float*, const float*, const float*, int, float*, const imdbn_update*, cudaStream_t) { return fail(ctx, -4, "tc path not built"); }
-void tc_destroy(imdbn_ctx*) {}
+
+SKPlan tc_plan(const imdbn_ctx* ctx, int M_total, int K_total) {
+    SKPlan p;
+    const int m_tiles = (M_total + TS_BM - 1) / TS_BM;
+    p.k_iters = (K_total + TS_BK - 1) / TS_BK;
+    const int total = m_tiles * p.k_iters;
+    const int G = std::min(ctx->num_sms, total);
+    p.q = total / G;
+    p.r = total % G;
+    p.tile_w = TS_BM;
+    return p;
+}
+
+int tc_plan_ctas(const SKPlan& p, int M_total) {
+    const int total = ((M_total + TS_BM - 1) / TS_BM) * p.k_iters;
+    return p.q > 0 ? (total - p.r) / p.q : total;      // total = G*q + r
+}
+
+int tc_plan_max_slabs(const SKPlan& p, int M_total) {
+    const int m_tiles = (M_total + TS_BM - 1) / TS_BM;
+    int mx = 1;
+    for (int t = 0; t < m_tiles; ++t) mx = std::max(mx, sk_nslabs(p, t));
+    return mx;
+}
+
+template <bool A_MN>
+static int launch_stream(imdbn_ctx* ctx, const CUtensorMap* tmA, const CUtensorMap* tmB, StreamArgs& a, int G,
+                         cudaStream_t st) {
+    const size_t smem = (size_t)a.stages * ts_stage_bytes(a.Npad) + 1024 + 256;
+    IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_tc_stream<A_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_tc_stream<A_MN><<<G, TS_THREADS, smem, st>>>(*tmA, *tmB, a);
+    IMDBN_CHECK_LAUNCH(ctx, "k_tc_stream");
+    return 0;
+}
+
+static int stream_pass(imdbn_ctx* ctx, const imdbn_rbm* r, const float* act, int B, float* part, bool up,
+                       cudaStream_t st) {
+    const int M_total = up ? r->H : r->V, K_total = up ? r->V : r->H;
+    if (!aligned16(act)) return fail(ctx, -1, "tc pass: activation pointer must be 16-byte aligned");
+    StreamArgs a{};
+    a.M_total = M_total; a.K_total = K_total; a.B = B; a.Npad = npad_of(B);
+    a.sk = tc_plan(ctx, M_total, K_total);
+    a.total_iters = ((M_total + TS_BM - 1) / TS_BM) * a.sk.k_iters;
+    a.part = part;
+    a.tmem_cols = pow2_cols(2 * a.Npad);
+    a.stages = std::max(2, std::min(TS_STAGES, (200 * 1024) / ts_stage_bytes(a.Npad)));
+    const int G = tc_plan_ctas(a.sk, M_total);
+    // W is [V, H] row-major: inner = H.  up: boxes [64 k-rows x 32 h]; down: boxes [128 v-rows x 32 h]
+    const CUtensorMap* tmA = get_map(ctx, r->W, r->H, r->V, up ? TS_BK : TS_BM, up);
+    const CUtensorMap* tmB = get_map(ctx, act, K_total, B, a.Npad, false);
+    if (!tmA || !tmB) return fail(ctx, -5, "cuTensorMapEncodeTiled failed");
+    return up ? launch_stream<true>(ctx, tmA, tmB, a, G, st) : launch_stream<false>(ctx, tmA, tmB, a, G, st);
+}
+
+int tc_gemm_up(imdbn_ctx* ctx, const imdbn_rbm* r, const float* v, int B, float* part, cudaStream_t st) {
+    return stream_pass(ctx, r, v, B, part, true, st);
+}
+int tc_gemm_down(imdbn_ctx* ctx, const imdbn_rbm* r, const float* h, int B, float* part, cudaStream_t st) {
+    return stream_pass(ctx, r, h, B, part, false, st);
+}
+
+int tc_gemm_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* vp, const float* hp, const float* vn,
+                  const float* hn, int B, float* dS_out, const imdbn_update* upd, cudaStream_t st) {
+    if (!aligned16(vp) || !aligned16(hp) || !aligned16(vn) || !aligned16(hn))
+        return fail(ctx, -1, "tc stats: activation pointers must be 16-byte aligned");
+    StatsArgs a{};
+    a.V = r->V; a.H = r->H; a.B = B;
+    a.m_tiles = (r->V + ST_BM - 1) / ST_BM;
+    a.n_tiles = (r->H + ST_BN - 1) / ST_BN;
+    a.k_chunks = (B + ST_KC - 1) / ST_KC;
+    a.W = r->W; a.Wm = r->Wm; a.dS = dS_out;
+    if (upd) { a.lr = upd->lr; a.mom = upd->momentum; a.wd = upd->weight_decay; a.bsz = (float)upd->batch_global; }
+    const CUtensorMap* tVP = get_map(ctx, vp, r->V, B, ST_KC, true);
+    const CUtensorMap* tVN = get_map(ctx, vn, r->V, B, ST_KC, true);
+    const CUtensorMap* tHP = get_map(ctx, hp, r->H, B, ST_KC, true);
+    const CUtensorMap* tHN = get_map(ctx, hn, r->H, B, ST_KC, true);
+    if (!tVP || !tVN || !tHP || !tHN) return fail(ctx, -5, "cuTensorMapEncodeTiled failed");
+    const int G = std::min(ctx->num_sms, a.m_tiles * a.n_tiles);
+    const size_t smem = (size_t)ST_STAGES * ST_STAGE_BYTES + ST_STG_BYTES + 1024 + 256;
+    if (dS_out) {
+        IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_tc_stats<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_tc_stats<false><<<G, ST_THREADS, smem, st>>>(*tVP, *tVN, *tHP, *tHN, a);
+    } else {
+        IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_tc_stats<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_tc_stats<true><<<G, ST_THREADS, smem, st>>>(*tVP, *tVN, *tHP, *tHN, a);
+    }
+    IMDBN_CHECK_LAUNCH(ctx, "k_tc_stats");
+    return 0;
+}
+
 }  // namespace imdbn

@@ -16,5 +16,8 @@ int tc_gemm_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* vp, const flo
                   const float* vn, const float* hn, int B, float* dS_out, const imdbn_update* upd,
                   cudaStream_t st);
 void tc_destroy(imdbn_ctx* ctx);
+// stream-K plan of a tensor-core pass producing M_total output features from K_total inputs
+SKPlan tc_plan(const imdbn_ctx* ctx, int M_total, int K_total);
+int tc_plan_max_slabs(const SKPlan& p, int M_total);
 
 }  // namespace imdbn

@@ -1,0 +1,114 @@
+"""GPU tests of the tensor-core path (precision 'tf32': tcgen05.mma kind::tf32, TMA-fed, TMEM
+accumulators).  Tolerance per north_star: activations / weights within 1e-3 of the fp32 reference
+(TF32 keeps 10 mantissa bits of W and of real-valued activations; accumulation is fp32)."""
+import ctypes as C
+
+import pytest
+import torch
+
+from oracle import rbm_oracle as O
+from oracle.philox import RandomField
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture()
+def M():
+    import multimodal_idbn_b200 as m
+    m.load_library()
+    m.set_precision("tf32")
+    yield m
+    m.set_precision("fp32")
+
+
+def make(M, V, H, seed=0, scale=1.0, groups=None):
+    st = O.new_state(V, H, seed=seed, groups=groups, lr=0.1, weight_decay=1e-4, momentum=0.5,
+                     final_momentum=0.95, dynamic_lr=True)
+    st.W *= scale
+    g = torch.Generator().manual_seed(seed + 1)
+    st.hb.copy_(torch.randn(H, generator=g) * 0.1); st.vb.copy_(torch.randn(V, generator=g) * 0.1)
+    r = M.RBM(V, H, 0.1, 1e-4, 0.5, dynamic_lr=True, final_momentum=0.95,
+              softmax_groups=list(groups or [])).to(DEV)
+    with torch.no_grad():
+        r.W.data.copy_(st.W); r.hid_bias.data.copy_(st.hb); r.vis_bias.data.copy_(st.vb)
+    return st, r
+
+
+SHAPES = [(10000, 1500), (1500, 500), (532, 256), (128, 128), (36, 20)]
+
+
+@pytest.mark.parametrize("V,H", SHAPES)
+@pytest.mark.parametrize("B", [1, 64, 130, 256])
+def test_up_down_tf32_vs_oracle(M, V, H, B):
+    st, r = make(M, V, H, seed=V + H)
+    gen = torch.Generator().manual_seed(B)
+    v = (torch.rand(B, V, generator=gen) < 0.3).float()
+    h = torch.rand(B, H, generator=gen)
+    p = r.forward(v.to(DEV))
+    torch.testing.assert_close(p.cpu(), O.hidden_probs(st, v), rtol=0, atol=1e-3)
+    pv = r.visible_probs(h.to(DEV))
+    torch.testing.assert_close(pv.cpu(), O.visible_probs(st, h), rtol=0, atol=1e-3)
+    # real-valued (non-binary) inputs, as test_extraction.py feeds (randn)
+    x = torch.randn(B, V, generator=gen)
+    torch.testing.assert_close(r.forward(x.to(DEV)).cpu(), O.hidden_probs(st, x), rtol=0, atol=2e-3)
+
+
+@pytest.mark.parametrize("V,H", SHAPES)
+@pytest.mark.parametrize("B", [1, 64, 100])
+def test_assoc_stats_tf32(M, V, H, B):
+    from multimodal_idbn_b200 import _lib as L
+    st, r = make(M, V, H, seed=3)
+    gen = torch.Generator().manual_seed(7)
+    vp = (torch.rand(B, V, generator=gen) < 0.3).float(); vn = (torch.rand(B, V, generator=gen) < 0.3).float()
+    hp = torch.rand(B, H, generator=gen); hn = torch.rand(B, H, generator=gen)
+    ref = vp.T @ hp - vn.T @ hn
+    out = torch.empty(V, H, device=DEV)
+    ctx, stream = L.context_for(out)
+    rs = r._struct()
+    d = [t.to(DEV).contiguous() for t in (vp, hp, vn, hn)]
+    ctx.check(ctx.lib.imdbn_assoc_stats(ctx.handle, C.byref(rs), L.ptr(d[0]), L.ptr(d[1]), L.ptr(d[2]),
+                                        L.ptr(d[3]), B, L.ptr(out), stream), "assoc")
+    # kind::tf32 reads the top 19 bits of every fp32 operand (truncation): emulate that exactly
+    def trunc(t):
+        return (t.view(torch.int32) & ~0x1FFF).view(torch.float32)
+    ref_t = trunc(vp).double().T @ trunc(hp).double() - trunc(vn).double().T @ trunc(hn).double()
+    torch.testing.assert_close(out.cpu().double(), ref_t, rtol=1e-5, atol=2e-5)
+    # and against the un-truncated product the error is the TF32 input rounding, ~2^-11 per term
+    assert float((out.cpu() - ref).abs().max()) < 2e-3 * max(4.0, 0.3 * B) ** 0.5 + 1e-3 * 0.3 * B
+
+
+def test_cd1_update_tf32_c1_shape(M):
+    V, H, B = 10000, 1500, 64
+    st, r = make(M, V, H, seed=11)
+    data = O.synthetic_images(B, V, seed=1234)
+    W0 = st.W.clone()
+    loss_ref, _ = O.cd_train(st, data, 0, 1, RandomField(5, 0))
+    r.set_rng(5, 0)
+    loss = r.train_epoch(data.to(DEV), 0, 1, CD=1)
+    torch.testing.assert_close(loss.cpu(), loss_ref, rtol=1e-3, atol=1e-6)
+    dW_ref = st.W - W0
+    dW = r.W.detach().cpu() - W0
+    # a few sampled units flip under TF32 (each flip moves one row / column of dS by lr/B); the bulk of
+    # the update must agree to 1e-3 of its scale
+    scale = float(dW_ref.abs().mean())
+    assert float((dW - dW_ref).abs().mean()) < 0.05 * scale
+    assert float(((dW - dW_ref).abs() > 1e-3 * 0.1).float().mean()) < 0.02
+    torch.testing.assert_close(r.hid_bias.detach().cpu(), st.hb, rtol=0, atol=2e-3)
+
+
+def test_tf32_and_fp32_modes_agree_on_a_training_run(M):
+    """50 CD-1 updates of a 532->256 joint-shaped RBM in both modes, same random field: the
+    reconstruction error curves must track each other (north_star: statistically matched)."""
+    V, H, B = 532, 256, 64
+    losses = {}
+    for mode in ("fp32", "tf32"):
+        M.set_precision(mode)
+        _, r = make(M, V, H, seed=5, scale=1.0)
+        r.set_rng(77, 0)
+        data = O.synthetic_images(B * 4, V, p=0.2, seed=3).to(DEV)
+        ls = [r.train_epoch(data[(i % 4) * B:(i % 4 + 1) * B], 0, 1, CD=1) for i in range(50)]
+        losses[mode] = torch.stack(ls).cpu()
+    M.set_precision("tf32")
+    assert losses["tf32"][-1] < losses["tf32"][0]
+    torch.testing.assert_close(losses["tf32"], losses["fp32"], rtol=2e-2, atol=1e-3)
