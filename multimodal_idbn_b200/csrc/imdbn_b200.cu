@@ -117,7 +117,7 @@ int up_pass(imdbn_ctx* ctx, const imdbn_rbm* r, const float* v, int B, float T, 
             cudaStream_t st) {
     int rc = gemm_up(ctx, r, v, B, pl, part, st);
     if (rc) return rc;
-    k_finish_up<<<ew_blocks((size_t)B * r->H, ctx->num_sms), 256, 0, st>>>(
+    k_finish_up<<<dim3((r->H + 255) / 256, std::min(B, 16384)), 256, 0, st>>>(
         part, pl.splits, pl.sk, B, r->H, r->hb, fmaxf(1e-6f, T), p_out, s_out, key, draw_u);
     IMDBN_CHECK_LAUNCH(ctx, "k_finish_up");
     return 0;
@@ -131,7 +131,7 @@ int down_pass(imdbn_ctx* ctx, const imdbn_rbm* r, const float* h, int B, float T
     if (rc) return rc;
     const Groups gr = make_groups(r);
     float* lg = logits_out ? logits_out : (gr.n ? logits_tmp : nullptr);
-    k_finish_down<<<ew_blocks((size_t)B * r->V, ctx->num_sms), 256, 0, st>>>(
+    k_finish_down<<<dim3((r->V + 255) / 256, std::min(B, 16384)), 256, 0, st>>>(
         part, pl.splits, pl.sk, B, r->V, r->vb, fmaxf(1e-6f, T), p_out, lg, s_out, key, draw_u);
     IMDBN_CHECK_LAUNCH(ctx, "k_finish_down");
     if (gr.n && (p_out || s_out)) {
@@ -156,25 +156,38 @@ int check_rbm(imdbn_ctx* ctx, const imdbn_rbm* r, bool need_momenta) {
     return 0;
 }
 
+inline int colstat_blocks(const imdbn_rbm* r) { return (std::max(r->V, r->H) + CS_COLS - 1) / CS_COLS; }
+
+// Column statistics into st_small = [dh | dv | sum pos_h | sq]; `apply` = also update the biases and
+// write the loss (single-GPU path); otherwise only the squared-error total is finalised.
 int finish_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* hp, const float* hn,
                  const float* vp, const float* vn, const float* ea, const float* eb, int B,
-                 float* st_small, float* sq_part, cudaStream_t st) {
-    const int cols = std::max(r->V, r->H);
-    const int nb = (cols + 255) / 256;
-    k_colstats<<<nb, 256, 0, st>>>(hp, hn, vp, vn, ea, eb, B, r->V, r->H, st_small, sq_part);
+                 float* st_small, float* sq_part, const imdbn_update* u, float* loss_out, bool apply,
+                 cudaStream_t st) {
+    const int nb = colstat_blocks(r);
+    k_colstats<<<nb, CS_COLS * CS_ROWS, 0, st>>>(hp, hn, vp, vn, ea, eb, B, r->V, r->H, st_small, sq_part);
     IMDBN_CHECK_LAUNCH(ctx, "k_colstats");
-    k_sum_partials<<<1, 256, 0, st>>>(sq_part, nb, st_small + 2 * r->H + r->V);
-    IMDBN_CHECK_LAUNCH(ctx, "k_sum_partials");
+    const int cols = std::max(r->V, r->H);
+    if (apply)
+        k_bias_update<<<(cols + 255) / 256, 256, 0, st>>>(
+            st_small, sq_part, nb, r->V, r->H, r->hb, r->hbm, r->vb, r->vbm, u->lr, u->momentum,
+            (float)u->batch_global, u->sparsity, u->sparsity_target, (float)u->batch_global * r->V,
+            loss_out, 1);
+    else
+        k_bias_update<<<1, 32, 0, st>>>(st_small, sq_part, nb, r->V, r->H, nullptr, nullptr, nullptr, nullptr,
+                                        0.f, 0.f, 1.f, 0, 0.f, 1.f, nullptr, 0);
+    IMDBN_CHECK_LAUNCH(ctx, "k_bias_update");
     return 0;
 }
 
-int bias_update(imdbn_ctx* ctx, const imdbn_rbm* r, const float* st_small, const imdbn_update* u,
+// bias update + loss from already reduced statistics (data-parallel path)
+int bias_update(imdbn_ctx* ctx, const imdbn_rbm* r, float* st_small, const imdbn_update* u,
                 float n_loss, float* loss_out, cudaStream_t st) {
     const int cols = std::max(r->V, r->H);
-    k_bias_update<<<(cols + 255) / 256, 256, 0, st>>>(st_small, r->V, r->H, r->hb, r->hbm, r->vb,
+    k_bias_update<<<(cols + 255) / 256, 256, 0, st>>>(st_small, nullptr, 0, r->V, r->H, r->hb, r->hbm, r->vb,
                                                       r->vbm, u->lr, u->momentum,
                                                       (float)u->batch_global, u->sparsity,
-                                                      u->sparsity_target, n_loss, loss_out);
+                                                      u->sparsity_target, n_loss, loss_out, 1);
     IMDBN_CHECK_LAUNCH(ctx, "k_bias_update");
     return 0;
 }
@@ -252,7 +265,7 @@ int cd_core(imdbn_ctx* ctx, const imdbn_rbm* r, const float* data, int B, int k,
     const int V = r->V, H = r->H;
     const PassPlan pu = plan_pass(ctx, r, B, true), pd = plan_pass(ctx, r, B, false);
     const size_t nBH = (size_t)B * H, nBV = (size_t)B * V;
-    const int nb_sq = (std::max(V, H) + 255) / 256;
+    const int nb_sq = colstat_blocks(r);
     size_t bytes = pad256(std::max(pu.part_floats, pd.part_floats)) + 3 * pad256(nBH) +
                    4 * pad256(nBV) + pad256(2 * H + V + 1) + pad256(nb_sq) +
                    tc_ws_bytes(ctx, r, B);
@@ -283,11 +296,8 @@ int cd_core(imdbn_ctx* ctx, const imdbn_rbm* r, const float* data, int B, int k,
     // update does not matter; keep the reference's order (weights first).
     rc = gemm_stats(ctx, r, data, pos_h, v_s, h_prob, B, stats_out, upd, st);           // :200,209,212
     if (rc) return rc;
-    rc = finish_stats(ctx, r, pos_h, h_prob, data, v_s, data, v_prob, B, st_small, sq_part, st);
-    if (rc) return rc;
-    if (!stats_out)
-        rc = bias_update(ctx, r, st_small, upd, (float)upd->batch_global * V, loss_out, st);
-    return rc;
+    return finish_stats(ctx, r, pos_h, h_prob, data, v_s, data, v_prob, B, st_small, sq_part, upd, loss_out,
+                        stats_out == nullptr, st);
 }
 
 int clamped_core(imdbn_ctx* ctx, const imdbn_rbm* r, const float* v_known, const float* km, int B,
@@ -301,7 +311,7 @@ int clamped_core(imdbn_ctx* ctx, const imdbn_rbm* r, const float* v_known, const
     IMDBN_ARG(ctx, n >= 0 && n <= CHAIN_MAX_STEPS);
     const PassPlan pu = plan_pass(ctx, r, B, true), pd = plan_pass(ctx, r, B, false);
     const size_t nBH = (size_t)B * H, nBV = (size_t)B * V;
-    const int nb_sq = (std::max(V, H) + 255) / 256;
+    const int nb_sq = colstat_blocks(r);
     size_t bytes = pad256(std::max(pu.part_floats, pd.part_floats)) + 3 * pad256(nBH) +
                    5 * pad256(nBV) + pad256(2 * H + V + 1) + pad256(nb_sq) +
                    pad256(chain_ws_floats(r, n)) + 1024 + tc_ws_bytes(ctx, r, B);
@@ -389,14 +399,10 @@ int clamped_core(imdbn_ctx* ctx, const imdbn_rbm* r, const float* v_known, const
     if (rc) return rc;
     rc = gemm_stats(ctx, r, v_plus, h_plus, v_neg, h_neg, B, stats_out, upd, st);       // :456,472,476
     if (rc) return rc;
-    rc = finish_stats(ctx, r, h_plus, h_neg, v_plus, v_neg, v_plus, v_neg, B, st_small, sq_part, st);
-    if (rc) return rc;
-    if (!stats_out) {
-        imdbn_update u = *upd;
-        u.sparsity = 0;                                                                 // :478-481
-        rc = bias_update(ctx, r, st_small, &u, (float)upd->batch_global * V, loss_out, st);
-    }
-    return rc;
+    imdbn_update u{};
+    if (upd) { u = *upd; u.sparsity = 0; }                                              // :478-481
+    return finish_stats(ctx, r, h_plus, h_neg, v_plus, v_neg, v_plus, v_neg, B, st_small, sq_part, &u,
+                        loss_out, stats_out == nullptr, st);
 }
 
 }  // namespace
@@ -572,7 +578,7 @@ int imdbn_apply_update(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* stats,
                                                                upd->momentum, upd->weight_decay,
                                                                (float)upd->batch_global);
     IMDBN_CHECK_LAUNCH(ctx, "k_weight_update");
-    return bias_update(ctx, rbm, stats + n, upd, (float)upd->batch_global * rbm->V, loss_out, st);
+    return bias_update(ctx, rbm, const_cast<float*>(stats) + n, upd, (float)upd->batch_global * rbm->V, loss_out, st);
 }
 
 int imdbn_assoc_stats(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* vp, const float* hp,

@@ -6,18 +6,27 @@
 
 namespace imdbn {
 
+// Rows on blockIdx.y (grid-stride), columns on blockIdx.x * blockDim.x + threadIdx.x: no integer
+// division on the element index.  `part` holds `splits` uniform K-split slabs (FFMA engine) or the
+// stream-K slabs of the tensor-core pass (SKPlan), summed here in a fixed order.
+__device__ __forceinline__ int finish_nslabs(const SKPlan& sk, int splits, int col) {
+    return sk.k_iters ? sk_nslabs(sk, col / sk.tile_w) : splits;
+}
+
 // ---- up pass finish: p = sigmoid((sum_s part + hb)/T), s = (p > U)           rbm.py:92,175,203
 __global__ void k_finish_up(const float* __restrict__ part, int splits, SKPlan sk, int B, int H,
                             const float* __restrict__ hb, float T, float* __restrict__ p_out,
                             float* __restrict__ s_out, RngKey key, uint32_t draw_u) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= H) return;
+    const int ns = finish_nslabs(sk, splits, j);
     const size_t n = (size_t)B * H;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
-         i += (size_t)gridDim.x * blockDim.x) {
-        const int b = (int)(i / H), j = (int)(i % H);
-        const int ns = sk.k_iters ? sk_nslabs(sk, j / sk.tile_w) : splits;
+    const float bj = hb[j];
+    for (int b = blockIdx.y; b < B; b += gridDim.y) {
+        const size_t i = (size_t)b * H + j;
         float x = 0.0f;
         for (int s = 0; s < ns; ++s) x += part[(size_t)s * n + i];
-        x = add_rn(x, hb[j]) / T;
+        x = add_rn(x, bj) / T;
         const float p = sigmoidf_ref(x);
         if (p_out) p_out[i] = p;
         if (s_out) s_out[i] = (p > rf_uniform(key, draw_u, b, j)) ? 1.0f : 0.0f;
@@ -30,14 +39,16 @@ __global__ void k_finish_down(const float* __restrict__ part, int splits, SKPlan
                               const float* __restrict__ vb, float T, float* __restrict__ p_out,
                               float* __restrict__ logits_out, float* __restrict__ s_out,
                               RngKey key, uint32_t draw_u) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= V) return;
+    const int ns = finish_nslabs(sk, splits, c);
     const size_t n = (size_t)B * V;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
-         i += (size_t)gridDim.x * blockDim.x) {
-        const int b = (int)(i / V), c = (int)(i % V);
-        const int ns = sk.k_iters ? sk_nslabs(sk, c / sk.tile_w) : splits;
+    const float bc = vb[c];
+    for (int b = blockIdx.y; b < B; b += gridDim.y) {
+        const size_t i = (size_t)b * V + c;
         float x = 0.0f;
         for (int s = 0; s < ns; ++s) x += part[(size_t)s * n + i];
-        x = add_rn(x, vb[c]) / T;
+        x = add_rn(x, bc) / T;
         if (logits_out) logits_out[i] = x;
         const float p = sigmoidf_ref(x);
         if (p_out) p_out[i] = p;
@@ -93,76 +104,81 @@ __global__ void k_groups(const float* __restrict__ logits, float* __restrict__ p
     }
 }
 
-// ---- column statistics of one CD step (rbm.py:216,223,226 / 478,480,483), one thread per column:
-//   out = [ dh (H) | dv (V) | pos_h column sum (H) | squared error (1) ]
+// ---- column statistics of one CD step (rbm.py:216,223,226 / 478,480,483)
+//   out = [ dh (H) | dv (V) | pos_h column sum (H) | squared error (1, written by k_bias_update) ]
 //   dh = sum_b hp - sum_b hn ; dv = sum_b vp - sum_b vn ; sq = sum (ea - eb)^2 over [B,V]
-__global__ void k_colstats(const float* __restrict__ hp, const float* __restrict__ hn,
-                           const float* __restrict__ vp, const float* __restrict__ vn,
-                           const float* __restrict__ ea, const float* __restrict__ eb, int B, int V,
-                           int H, float* __restrict__ out, float* __restrict__ sq_part) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    float sq = 0.0f;
-    if (c < H) {
-        float a = 0.0f, n = 0.0f;
-        for (int b = 0; b < B; ++b) { a += hp[(size_t)b * H + c]; n += hn[(size_t)b * H + c]; }
-        out[c] = a - n;
-        out[H + V + c] = a;
-    }
-    if (c < V) {
-        float a = 0.0f, n = 0.0f;
-        for (int b = 0; b < B; ++b) {
+// Block = 32 columns x 8 row lanes; every thread sums rows y, y+8, ...; the 8 lane sums are added in
+// lane order (deterministic).  One squared-error partial per block.
+constexpr int CS_COLS = 32, CS_ROWS = 8;
+__global__ void __launch_bounds__(CS_COLS * CS_ROWS)
+k_colstats(const float* __restrict__ hp, const float* __restrict__ hn, const float* __restrict__ vp,
+           const float* __restrict__ vn, const float* __restrict__ ea, const float* __restrict__ eb, int B,
+           int V, int H, float* __restrict__ out, float* __restrict__ sq_part) {
+    __shared__ float red[5][CS_ROWS][CS_COLS];
+    const int x = threadIdx.x % CS_COLS, y = threadIdx.x / CS_COLS;
+    const int c = blockIdx.x * CS_COLS + x;
+    float ha = 0.f, hb_ = 0.f, va = 0.f, vb_ = 0.f, sq = 0.f;
+    if (c < H)
+        for (int b = y; b < B; b += CS_ROWS) { ha += hp[(size_t)b * H + c]; hb_ += hn[(size_t)b * H + c]; }
+    if (c < V)
+        for (int b = y; b < B; b += CS_ROWS) {
             const size_t o = (size_t)b * V + c;
-            a += vp[o]; n += vn[o];
+            va += vp[o]; vb_ += vn[o];
             const float d = ea[o] - eb[o];
             sq = fmaf(d, d, sq);
         }
-        out[H + c] = a - n;
-    }
-    // deterministic block sum of the squared error -> one partial per block
-    __shared__ float red[32];
-    for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+    red[0][y][x] = ha; red[1][y][x] = hb_; red[2][y][x] = va; red[3][y][x] = vb_; red[4][y][x] = sq;
     __syncthreads();
-    if (threadIdx.x < 32) {
-        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0f;
-        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (threadIdx.x == 0) sq_part[blockIdx.x] = v;
+    if (y == 0) {
+        float t[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            float a = 0.f;
+#pragma unroll
+            for (int r = 0; r < CS_ROWS; ++r) a += red[q][r][x];
+            t[q] = a;
+        }
+        if (c < H) { out[c] = t[0] - t[1]; out[H + V + c] = t[0]; }
+        if (c < V) out[H + c] = t[2] - t[3];
+        float s = t[4];
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (x == 0) sq_part[blockIdx.x] = s;
     }
 }
 
-// sum the per-block partials in index order (single block)
-__global__ void k_sum_partials(const float* __restrict__ part, int n, float* __restrict__ out) {
-    __shared__ float red[32];
-    float v = 0.0f;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) v += part[i];
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0f;
-        for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (threadIdx.x == 0) *out = t;
-    }
-}
-
-// ---- bias updates (rbm.py:216-224 / 478-481) and the loss (rbm.py:226 / 483)
-__global__ void k_bias_update(const float* __restrict__ st, int V, int H, float* __restrict__ hb,
-                              float* __restrict__ hbm, float* __restrict__ vb, float* __restrict__ vbm,
-                              float lr, float mom, float bsz, int sparsity, float sp_target,
-                              float n_loss, float* __restrict__ loss_out) {
+// ---- bias updates (rbm.py:216-224 / 478-481) and the loss (rbm.py:226 / 483).  Block 0 also adds the
+// squared-error partials in index order (when sq_part != nullptr) and stores the total in st[2H+V].
+__global__ void k_bias_update(float* __restrict__ st, const float* __restrict__ sq_part, int n_part, int V,
+                              int H, float* __restrict__ hb, float* __restrict__ hbm, float* __restrict__ vb,
+                              float* __restrict__ vbm, float lr, float mom, float bsz, int sparsity,
+                              float sp_target, float n_loss, float* __restrict__ loss_out, int apply) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < H) {
-        float m = add_rn(mul_rn(hbm[c], mom), mul_rn(lr, st[c]) / bsz);
-        if (sparsity) m = add_rn(m, mul_rn(-lr, add_rn(st[H + V + c] / bsz, -sp_target)));
-        hbm[c] = m;
-        hb[c] = add_rn(hb[c], m);
+    if (apply) {
+        if (c < H) {
+            float m = add_rn(mul_rn(hbm[c], mom), mul_rn(lr, st[c]) / bsz);
+            if (sparsity) m = add_rn(m, mul_rn(-lr, add_rn(st[H + V + c] / bsz, -sp_target)));
+            hbm[c] = m;
+            hb[c] = add_rn(hb[c], m);
+        }
+        if (c < V) {
+            const float m = add_rn(mul_rn(vbm[c], mom), mul_rn(lr, st[H + c]) / bsz);
+            vbm[c] = m;
+            vb[c] = add_rn(vb[c], m);
+        }
     }
-    if (c < V) {
-        const float m = add_rn(mul_rn(vbm[c], mom), mul_rn(lr, st[H + c]) / bsz);
-        vbm[c] = m;
-        vb[c] = add_rn(vb[c], m);
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+        float total;
+        if (sq_part) {
+            float v = 0.f;
+            for (int i = threadIdx.x; i < n_part; i += 32) v += sq_part[i];
+            for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            total = v;
+            if (threadIdx.x == 0) st[2 * H + V] = total;
+        } else {
+            total = st[2 * H + V];
+        }
+        if (threadIdx.x == 0 && loss_out) *loss_out = total / n_loss;
     }
-    if (c == 0 && loss_out) *loss_out = st[2 * H + V] / n_loss;
 }
 
 // element-wise weight update from an (all-reduced) dS                          rbm.py:212-213

@@ -246,195 +246,7 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// CD statistics + update kernel
-// ------------------------------------------------------------------------------------------------
-constexpr int ST_BM = 128;                 // visible units per tile (MMA M)
-constexpr int ST_BN = 128;                 // hidden units per tile  (MMA N)
-constexpr int ST_KC = 32;                  // batch rows per pipeline stage and segment
-constexpr int ST_STAGES = 2;
-constexpr int ST_EPI_WARPS = 8;
-constexpr int ST_THREADS = 64 + ST_EPI_WARPS * 32;
-constexpr int ST_SEG_A = ST_BM * ST_KC * 4;          // 16 KB: 4 boxes [32 rows x 128 B]
-constexpr int ST_SEG_B = ST_BN * ST_KC * 4;          // 16 KB
-constexpr int ST_STAGE_BYTES = 2 * (ST_SEG_A + ST_SEG_B);   // positive + negative phase
-constexpr int ST_STG_LD = 65;                        // staging row stride (floats), 64 columns per warp
-constexpr int ST_STG_BYTES = ST_EPI_WARPS * 32 * ST_STG_LD * 4;
-
-struct StatsArgs {
-    int V, H, B;
-    int m_tiles, n_tiles, k_chunks;
-    float* W; float* Wm; float* dS;
-    float lr, mom, wd, bsz;
-};
-
-template <bool UPDATE>
-__global__ void __launch_bounds__(ST_THREADS, 1)
-k_tc_stats(const __grid_constant__ CUtensorMap tmVP, const __grid_constant__ CUtensorMap tmVN,
-           const __grid_constant__ CUtensorMap tmHP, const __grid_constant__ CUtensorMap tmHN, StatsArgs a) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    float* staging = reinterpret_cast<float*>(smem + ST_STAGES * ST_STAGE_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ST_STAGES * ST_STAGE_BYTES + ST_STG_BYTES);
-    uint64_t* full = bars;
-    uint64_t* empty = bars + ST_STAGES;
-    uint64_t* acc_full = bars + 2 * ST_STAGES;
-    uint64_t* acc_empty = acc_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_tiles_total = a.m_tiles * a.n_tiles;
-    // contiguous, balanced tile ranges (consecutive tiles share the visible block -> L2-friendly)
-    const int q = n_tiles_total / gridDim.x, r = n_tiles_total % gridDim.x;
-    const int t_beg = blockIdx.x * q + min((int)blockIdx.x, r);
-    const int t_end = t_beg + q + ((int)blockIdx.x < r ? 1 : 0);
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmVP); tma_prefetch_desc(&tmVN); tma_prefetch_desc(&tmHP); tma_prefetch_desc(&tmHN);
-        for (int s = 0; s < ST_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], ST_EPI_WARPS); }
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc(tmem_slot, 2 * ST_BN);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        if (elect_one()) {
-            int stage = 0; uint32_t phase = 0;
-            for (int t = t_beg; t < t_end; ++t) {
-                const int m0 = (t / a.n_tiles) * ST_BM, n0 = (t % a.n_tiles) * ST_BN;
-                for (int kc = 0; kc < a.k_chunks; ++kc) {
-                    const int b0 = kc * ST_KC;
-                    uint8_t* s0 = smem + stage * ST_STAGE_BYTES;
-                    mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_expect_tx(&full[stage], ST_STAGE_BYTES);
-#pragma unroll
-                    for (int cb = 0; cb < ST_BM / 32; ++cb) {
-                        tma_load_2d(s0 + cb * 4096, &tmVP, m0 + cb * 32, b0, &full[stage]);
-                        tma_load_2d(s0 + ST_SEG_A + cb * 4096, &tmVN, m0 + cb * 32, b0, &full[stage]);
-                    }
-#pragma unroll
-                    for (int cb = 0; cb < ST_BN / 32; ++cb) {
-                        tma_load_2d(s0 + 2 * ST_SEG_A + cb * 4096, &tmHP, n0 + cb * 32, b0, &full[stage]);
-                        tma_load_2d(s0 + 2 * ST_SEG_A + ST_SEG_B + cb * 4096, &tmHN, n0 + cb * 32, b0, &full[stage]);
-                    }
-                    if (++stage == ST_STAGES) { stage = 0; phase ^= 1; }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (elect_one()) {
-            const uint32_t id_pos = idesc_tf32(ST_BM, ST_BN, true, true, false);
-            const uint32_t id_neg = idesc_tf32(ST_BM, ST_BN, true, true, true);     // -A * B
-            int stage = 0; uint32_t phase = 0;
-            int seg = 0;
-            for (int t = t_beg; t < t_end; ++t, ++seg) {
-                const int buf = seg & 1;
-                mbar_wait(&acc_empty[buf], ((seg >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ST_BN);
-                for (int kc = 0; kc < a.k_chunks; ++kc) {
-                    mbar_wait(&full[stage], phase);
-                    tc_fence_after();
-                    const uint32_t s0 = smem_u32(smem + stage * ST_STAGE_BYTES);
-#pragma unroll
-                    for (int g = 0; g < ST_KC / 8; ++g) {
-                        const uint64_t ap = smem_desc(s0 + g * 1024, 4096, 512, LAYOUT_SW128_BASE32B);
-                        const uint64_t an = smem_desc(s0 + ST_SEG_A + g * 1024, 4096, 512, LAYOUT_SW128_BASE32B);
-                        const uint64_t bp = smem_desc(s0 + 2 * ST_SEG_A + g * 1024, 4096, 512, LAYOUT_SW128_BASE32B);
-                        const uint64_t bn = smem_desc(s0 + 2 * ST_SEG_A + ST_SEG_B + g * 1024, 4096, 512,
-                                                      LAYOUT_SW128_BASE32B);
-                        mma_tf32(d_tmem, ap, bp, id_pos, (kc | g) != 0);
-                        mma_tf32(d_tmem, an, bn, id_neg, 1u);
-                    }
-                    mma_commit(&empty[stage]);
-                    if (++stage == ST_STAGES) { stage = 0; phase ^= 1; }
-                }
-                mma_commit(&acc_full[buf]);
-            }
-        }
-    } else {
-        // ===================== epilogue =====================
-        const int e = warp - 2;                       // 0..7
-        const int quad = warp & 3;                    // TMEM lane quadrant
-        const int half = e >> 2;                      // which 64-column half of the tile
-        float* stg = staging + e * 32 * ST_STG_LD;
-        int seg = 0;
-        for (int t = t_beg; t < t_end; ++t, ++seg) {
-            const int buf = seg & 1;
-            const int m0 = (t / a.n_tiles) * ST_BM + quad * 32;
-            const int n0 = (t % a.n_tiles) * ST_BN + half * 64;
-            mbar_wait(&acc_full[buf], (seg >> 1) & 1);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * ST_BN + half * 64);
-#pragma unroll
-            for (int c0 = 0; c0 < 64; c0 += 16) {
-                float v[16];
-                tmem_ld16(taddr + c0, v);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) stg[lane * ST_STG_LD + c0 + i] = v[i];
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[buf]);   // accumulator drained: MMA may reuse it
-
-            // rows of this warp's 32 x 64 sub-tile, lanes along the hidden (contiguous) dimension
-            const int h_a = n0 + lane, h_b = n0 + 32 + lane;
-            const bool ok_a = h_a < a.H, ok_b = h_b < a.H;
-#pragma unroll 1
-            for (int r0 = 0; r0 < 32; r0 += 8) {
-                float w[8][2], wm[8][2];
-                if (UPDATE) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int row = m0 + r0 + i;
-                        const size_t o = (size_t)row * a.H;
-                        const bool rok = row < a.V;
-                        w[i][0] = (rok && ok_a) ? a.W[o + h_a] : 0.f;
-                        w[i][1] = (rok && ok_b) ? a.W[o + h_b] : 0.f;
-                        wm[i][0] = (rok && ok_a) ? a.Wm[o + h_a] : 0.f;
-                        wm[i][1] = (rok && ok_b) ? a.Wm[o + h_b] : 0.f;
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int row = m0 + r0 + i;
-                    if (row >= a.V) continue;
-                    const size_t o = (size_t)row * a.H;
-                    const float s_a = stg[(r0 + i) * ST_STG_LD + lane];
-                    const float s_b = stg[(r0 + i) * ST_STG_LD + 32 + lane];
-                    if (UPDATE) {
-                        // W_m <- mom*W_m + lr*((S+ - S-)/bsz - wd*W);  W <- W + W_m   (rbm.py:212-213)
-                        if (ok_a) {
-                            const float g = add_rn(s_a / a.bsz, -mul_rn(a.wd, w[i][0]));
-                            const float m = add_rn(mul_rn(wm[i][0], a.mom), mul_rn(a.lr, g));
-                            a.Wm[o + h_a] = m; a.W[o + h_a] = add_rn(w[i][0], m);
-                        }
-                        if (ok_b) {
-                            const float g = add_rn(s_b / a.bsz, -mul_rn(a.wd, w[i][1]));
-                            const float m = add_rn(mul_rn(wm[i][1], a.mom), mul_rn(a.lr, g));
-                            a.Wm[o + h_b] = m; a.W[o + h_b] = add_rn(w[i][1], m);
-                        }
-                    } else {
-                        if (ok_a) a.dS[o + h_a] = s_a;
-                        if (ok_b) a.dS[o + h_b] = s_b;
-                    }
-                }
-            }
-            __syncwarp();     // staging is rewritten by the next tile
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, 2 * ST_BN);
-    }
-}
+#include "tc_stats.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // host side
@@ -518,28 +330,30 @@ int tc_gemm_down(imdbn_ctx* ctx, const imdbn_rbm* r, const float* h, int B, floa
 
 int tc_gemm_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* vp, const float* hp, const float* vn,
                   const float* hn, int B, float* dS_out, const imdbn_update* upd, cudaStream_t st) {
-    if (!aligned16(vp) || !aligned16(hp) || !aligned16(vn) || !aligned16(hn))
-        return fail(ctx, -1, "tc stats: activation pointers must be 16-byte aligned");
+    if (!aligned16(vp) || !aligned16(hp) || !aligned16(vn) || !aligned16(hn) || (dS_out && !aligned16(dS_out)) ||
+        (!dS_out && !aligned16(r->Wm)))
+        return fail(ctx, -1, "tc stats: pointers must be 16-byte aligned");
     StatsArgs a{};
     a.V = r->V; a.H = r->H; a.B = B;
     a.m_tiles = (r->V + ST_BM - 1) / ST_BM;
     a.n_tiles = (r->H + ST_BN - 1) / ST_BN;
     a.k_chunks = (B + ST_KC - 1) / ST_KC;
-    a.W = r->W; a.Wm = r->Wm; a.dS = dS_out;
     if (upd) { a.lr = upd->lr; a.mom = upd->momentum; a.wd = upd->weight_decay; a.bsz = (float)upd->batch_global; }
+    a.dbg = 0;
     const CUtensorMap* tVP = get_map(ctx, vp, r->V, B, ST_KC, true);
     const CUtensorMap* tVN = get_map(ctx, vn, r->V, B, ST_KC, true);
     const CUtensorMap* tHP = get_map(ctx, hp, r->H, B, ST_KC, true);
     const CUtensorMap* tHN = get_map(ctx, hn, r->H, B, ST_KC, true);
-    if (!tVP || !tVN || !tHP || !tHN) return fail(ctx, -5, "cuTensorMapEncodeTiled failed");
+    const CUtensorMap* tW = get_map(ctx, dS_out ? dS_out : r->W, r->H, r->V, ST_BM, false);
+    const CUtensorMap* tWm = dS_out ? tW : get_map(ctx, r->Wm, r->H, r->V, ST_BM, false);
+    if (!tVP || !tVN || !tHP || !tHN || !tW || !tWm) return fail(ctx, -5, "cuTensorMapEncodeTiled failed");
     const int G = std::min(ctx->num_sms, a.m_tiles * a.n_tiles);
-    const size_t smem = (size_t)ST_STAGES * ST_STAGE_BYTES + ST_STG_BYTES + 1024 + 256;
     if (dS_out) {
-        IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_tc_stats<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_tc_stats<false><<<G, ST_THREADS, smem, st>>>(*tVP, *tVN, *tHP, *tHN, a);
+        IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_tc_stats<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
+        k_tc_stats<false><<<G, ST_THREADS, ST_SMEM, st>>>(*tVP, *tVN, *tHP, *tHN, *tW, *tWm, a);
     } else {
-        IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_tc_stats<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_tc_stats<true><<<G, ST_THREADS, smem, st>>>(*tVP, *tVN, *tHP, *tHN, a);
+        IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_tc_stats<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
+        k_tc_stats<true><<<G, ST_THREADS, ST_SMEM, st>>>(*tVP, *tVN, *tHP, *tHN, *tW, *tWm, a);
     }
     IMDBN_CHECK_LAUNCH(ctx, "k_tc_stats");
     return 0;

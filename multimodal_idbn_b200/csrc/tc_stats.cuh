@@ -1,0 +1,254 @@
+// CD statistics + update kernel (included by tc_gemm.cu).
+//
+//   dS[v,h] = sum_b vp[b,v] hp[b,h] - sum_b vn[b,v] hn[b,h]              (rbm.py:200,209)
+//   W_m <- mom W_m + lr (dS/bsz - wd W) ;  W <- W + W_m                   (rbm.py:212-213)
+//
+// Output-streaming and HBM-bound at small batch: per 128 x 128 tile the kernel reads and writes
+// 2 x 64 KB of W / W_m and needs only 16 tf32 MMAs.  Every byte therefore moves through TMA:
+//   * operand producer (warp 0): [16 batch rows x 32] boxes of vp, vn, hp, hn (MN-major, 32-byte-atom
+//     swizzle) into a 2-stage ring;
+//   * MMA issuer (warp 1): 128x128x8 tcgen05.mma kind::tf32 into one of two TMEM accumulators; the
+//     negative phase is subtracted with the a_negate bit;
+//   * IO producer (warp 2): the W and W_m half-tiles (128 rows x 64 columns each) into one of two 64 KB
+//     slots -- up to 128 KB of weight traffic in flight per SM, independent of the math warps;
+//   * epilogue (warps 4-11): thread = tile row; accumulator from TMEM, W / W_m from the swizzled slot
+//     (bank-conflict-free with one row per lane), update written back in place;
+//   * store issuer (warp 3): TMA-stores the slot back to W / W_m (edges are clipped by the tensor map)
+//     and releases the slot when the store has drained shared memory.
+#pragma once
+
+constexpr int ST_BM = 128;                 // visible units per tile (MMA M)
+constexpr int ST_BN = 128;                 // hidden units per tile  (MMA N)
+constexpr int ST_KC = 16;                  // batch rows per operand stage
+constexpr int ST_STAGES = 2;
+constexpr int ST_THREADS = 384;            // 12 warps, roles above
+constexpr int ST_EPI_WARPS = 8;
+constexpr int ST_OP_BOX = ST_KC * 128;                 // one [16 x 32 floats] box = 2 KB
+constexpr int ST_SEG_A = (ST_BM / 32) * ST_OP_BOX;     // 8 KB
+constexpr int ST_SEG_B = (ST_BN / 32) * ST_OP_BOX;     // 8 KB
+constexpr int ST_STAGE_BYTES = 2 * (ST_SEG_A + ST_SEG_B);   // positive + negative phase: 32 KB
+constexpr int ST_IO_BOX = ST_BM * 128;                 // [128 rows x 32 floats] = 16 KB
+constexpr int ST_NSLOT = 4;                            // IO slots (power of two)
+constexpr int ST_SLOT_BYTES = 2 * ST_IO_BOX;           // W + W_m quarter-tile [128 x 32] each: 32 KB
+constexpr int ST_SMEM = ST_STAGES * ST_STAGE_BYTES + ST_NSLOT * ST_SLOT_BYTES + 1024 /*barriers*/ + 1024 /*align*/;
+
+struct StatsArgs {
+    int V, H, B;
+    int m_tiles, n_tiles, k_chunks;
+    float lr, mom, wd, bsz;
+    int dbg;    // experiment switch (IMDBN_DEBUG_STATS): 1 = no operands/MMA, 2 = no W/W_m traffic
+};
+
+template <bool UPDATE>
+__global__ void __launch_bounds__(ST_THREADS, 1)
+k_tc_stats(const __grid_constant__ CUtensorMap tmVP, const __grid_constant__ CUtensorMap tmVN,
+           const __grid_constant__ CUtensorMap tmHP, const __grid_constant__ CUtensorMap tmHN,
+           const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWm, StatsArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* ops = smem;                                       // operand ring
+    uint8_t* slots = smem + ST_STAGES * ST_STAGE_BYTES;        // 2 IO slots
+    uint64_t* bars = reinterpret_cast<uint64_t*>(slots + ST_NSLOT * ST_SLOT_BYTES);
+    uint64_t* ops_full = bars;            // [2]
+    uint64_t* ops_empty = bars + 2;       // [2]
+    uint64_t* acc_full = bars + 4;        // [2]
+    uint64_t* acc_empty = bars + 6;       // [2]
+    uint64_t* io_full = bars + 8;         // [ST_NSLOT]
+    uint64_t* io_written = bars + 12;     // [ST_NSLOT]
+    uint64_t* io_empty = bars + 16;       // [ST_NSLOT]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles_total = a.m_tiles * a.n_tiles;
+    // Round-robin tile order: at any moment the CTAs of the grid work on CONSECUTIVE tiles, i.e. on
+    // adjacent column blocks of the same 128 weight rows, so DRAM sees whole rows streamed together
+    // (row-buffer locality) instead of 512-byte fragments.
+    const int t_beg = blockIdx.x, t_end = n_tiles_total, t_step = gridDim.x;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmVP); tma_prefetch_desc(&tmVN); tma_prefetch_desc(&tmHP); tma_prefetch_desc(&tmHN);
+        tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmWm);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&ops_full[s], 1); mbar_init(&ops_empty[s], 1);
+            mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], ST_EPI_WARPS);
+        }
+        for (int s = 0; s < ST_NSLOT; ++s) {
+            mbar_init(&io_full[s], 1); mbar_init(&io_written[s], ST_EPI_WARPS / 2); mbar_init(&io_empty[s], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * ST_BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== operand producer =====================
+        if (a.dbg != 1 && elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = t_beg; t < t_end; t += t_step) {
+                const int m0 = (t / a.n_tiles) * ST_BM, n0 = (t % a.n_tiles) * ST_BN;
+                for (int kc = 0; kc < a.k_chunks; ++kc) {
+                    const int b0 = kc * ST_KC;
+                    uint8_t* s0 = ops + stage * ST_STAGE_BYTES;
+                    mbar_wait(&ops_empty[stage], phase ^ 1);
+                    mbar_expect_tx(&ops_full[stage], ST_STAGE_BYTES);
+#pragma unroll
+                    for (int cb = 0; cb < ST_BM / 32; ++cb) {
+                        tma_load_2d(s0 + cb * ST_OP_BOX, &tmVP, m0 + cb * 32, b0, &ops_full[stage]);
+                        tma_load_2d(s0 + ST_SEG_A + cb * ST_OP_BOX, &tmVN, m0 + cb * 32, b0, &ops_full[stage]);
+                    }
+#pragma unroll
+                    for (int cb = 0; cb < ST_BN / 32; ++cb) {
+                        tma_load_2d(s0 + 2 * ST_SEG_A + cb * ST_OP_BOX, &tmHP, n0 + cb * 32, b0, &ops_full[stage]);
+                        tma_load_2d(s0 + 2 * ST_SEG_A + ST_SEG_B + cb * ST_OP_BOX, &tmHN, n0 + cb * 32, b0,
+                                    &ops_full[stage]);
+                    }
+                    if (++stage == ST_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (a.dbg != 1 && elect_one()) {
+            const uint32_t id_pos = idesc_tf32(ST_BM, ST_BN, true, true, false);
+            const uint32_t id_neg = idesc_tf32(ST_BM, ST_BN, true, true, true);     // (-A) * B
+            int stage = 0; uint32_t phase = 0;
+            int seg = 0;
+            for (int t = t_beg; t < t_end; t += t_step, ++seg) {
+                const int buf = seg & 1;
+                mbar_wait(&acc_empty[buf], ((seg >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ST_BN);
+                for (int kc = 0; kc < a.k_chunks; ++kc) {
+                    mbar_wait(&ops_full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t s0 = smem_u32(ops + stage * ST_STAGE_BYTES);
+#pragma unroll
+                    for (int g = 0; g < ST_KC / 8; ++g) {
+                        const uint64_t ap = smem_desc(s0 + g * 1024, ST_OP_BOX, 512, LAYOUT_SW128_BASE32B);
+                        const uint64_t an = smem_desc(s0 + ST_SEG_A + g * 1024, ST_OP_BOX, 512, LAYOUT_SW128_BASE32B);
+                        const uint64_t bp = smem_desc(s0 + 2 * ST_SEG_A + g * 1024, ST_OP_BOX, 512, LAYOUT_SW128_BASE32B);
+                        const uint64_t bn = smem_desc(s0 + 2 * ST_SEG_A + ST_SEG_B + g * 1024, ST_OP_BOX, 512,
+                                                      LAYOUT_SW128_BASE32B);
+                        mma_tf32(d_tmem, ap, bp, id_pos, (kc | g) != 0);
+                        mma_tf32(d_tmem, an, bn, id_neg, 1u);
+                    }
+                    mma_commit(&ops_empty[stage]);
+                    if (++stage == ST_STAGES) { stage = 0; phase ^= 1; }
+                }
+                mma_commit(&acc_full[buf]);
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== IO producer: W / W_m quarter-tiles (128 rows x 32 columns) ============
+        if (UPDATE && a.dbg != 2 && a.dbg != 4 && elect_one()) {
+            int hh = 0;
+            for (int t = t_beg; t < t_end; t += t_step) {
+                const int m0 = (t / a.n_tiles) * ST_BM, n0 = (t % a.n_tiles) * ST_BN;
+                for (int qt = 0; qt < 4; ++qt, ++hh) {
+                    const int s = hh & (ST_NSLOT - 1);
+                    uint8_t* slot = slots + s * ST_SLOT_BYTES;
+                    mbar_wait(&io_empty[s], ((hh / ST_NSLOT) & 1) ^ 1);
+                    mbar_expect_tx(&io_full[s], ST_SLOT_BYTES);
+                    tma_load_2d(slot, &tmW, n0 + qt * 32, m0, &io_full[s]);
+                    tma_load_2d(slot + ST_IO_BOX, &tmWm, n0 + qt * 32, m0, &io_full[s]);
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ===================== store issuer =====================
+        if (a.dbg != 2 && elect_one()) {
+            int hh = 0;
+            for (int t = t_beg; t < t_end; t += t_step) {
+                const int m0 = (t / a.n_tiles) * ST_BM, n0 = (t % a.n_tiles) * ST_BN;
+                for (int qt = 0; qt < 4; ++qt, ++hh) {
+                    const int s = hh & (ST_NSLOT - 1);
+                    const uint8_t* slot = slots + s * ST_SLOT_BYTES;
+                    mbar_wait(&io_written[s], (hh / ST_NSLOT) & 1);
+                    if (a.dbg != 3) {
+                        tma_store_2d(&tmW, n0 + qt * 32, m0, slot);
+                        if (UPDATE) tma_store_2d(&tmWm, n0 + qt * 32, m0, slot + ST_IO_BOX);
+                    }
+                    tma_store_commit();
+                    tma_store_wait_read();            // shared memory of the slot may be overwritten
+                    mbar_arrive(&io_empty[s]);
+                }
+            }
+            tma_store_wait_all();                     // global writes complete before the kernel ends
+        }
+    } else {
+        // ===================== epilogue =====================
+        // Two groups of four warps; group g owns the quarter-tiles g and g+2 of every tile.  Inside a
+        // group, warp <-> TMEM lane quadrant, thread <-> tile row.
+        const int quad = warp & 3;
+        const int grp = (warp - 4) >> 2;
+        const int row = quad * 32 + lane;
+        const uint32_t sw = (uint32_t)(row & 7);      // 128-byte-swizzle phase of this row
+        int seg = 0;
+        for (int t = t_beg; t < t_end; t += t_step, ++seg) {
+            const int buf = seg & 1;
+            if (a.dbg != 1) mbar_wait(&acc_full[buf], (seg >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int qi = 0; qi < 2; ++qi) {
+                const int qt = grp + 2 * qi;
+                const int hh = seg * 4 + qt;
+                const int s = hh & (ST_NSLOT - 1);
+                uint8_t* wrow = slots + s * ST_SLOT_BYTES + row * 128;
+                uint8_t* mrow = wrow + ST_IO_BOX;
+                float acc[32];
+                {
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * ST_BN + qt * 32);
+                    float v0[16], v1[16];
+                    tmem_ld16(taddr, v0);
+                    tmem_ld16(taddr + 16, v1);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { acc[i] = v0[i]; acc[16 + i] = v1[i]; }
+                }
+                if (qi == 1) {                         // this warp has read its share of the accumulator
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                }
+                if (a.dbg == 2) continue;
+                if (UPDATE && a.dbg != 4) mbar_wait(&io_full[s], (hh / ST_NSLOT) & 1);
+                else                      mbar_wait(&io_empty[s], ((hh / ST_NSLOT) & 1) ^ 1);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t off = ((uint32_t)j ^ sw) << 4;
+                    float4* wp = reinterpret_cast<float4*>(wrow + off);
+                    if (UPDATE) {
+                        float4* mp = reinterpret_cast<float4*>(mrow + off);
+                        const float4 w4 = *wp, m4 = *mp;
+                        const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+                        const float mv[4] = {m4.x, m4.y, m4.z, m4.w};
+                        float nw[4], nm[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            // W_m <- mom*W_m + lr*((S+ - S-)/bsz - wd*W);  W <- W + W_m
+                            const float g = add_rn(acc[4 * j + e] / a.bsz, -mul_rn(a.wd, wv[e]));
+                            nm[e] = add_rn(mul_rn(mv[e], a.mom), mul_rn(a.lr, g));
+                            nw[e] = add_rn(wv[e], nm[e]);
+                        }
+                        *mp = make_float4(nm[0], nm[1], nm[2], nm[3]);
+                        *wp = make_float4(nw[0], nw[1], nw[2], nw[3]);
+                    } else {
+                        *wp = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+                    }
+                }
+                fence_proxy_async();                   // generic-proxy writes -> visible to the TMA store
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&io_written[s]);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 2 * ST_BN);
+    }
+}
