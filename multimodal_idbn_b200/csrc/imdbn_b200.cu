@@ -165,18 +165,17 @@ int finish_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* hp, const floa
                  float* st_small, float* sq_part, const imdbn_update* u, float* loss_out, bool apply,
                  cudaStream_t st) {
     const int nb = colstat_blocks(r);
-    k_colstats<<<nb, CS_COLS * CS_ROWS, 0, st>>>(hp, hn, vp, vn, ea, eb, B, r->V, r->H, st_small, sq_part);
+    BiasArgs ba{};
+    if (apply) {
+        ba.apply = 1;
+        ba.hb = r->hb; ba.hbm = r->hbm; ba.vb = r->vb; ba.vbm = r->vbm;
+        ba.lr = u->lr; ba.mom = u->momentum; ba.bsz = (float)u->batch_global;
+        ba.sparsity = u->sparsity; ba.sp_target = u->sparsity_target;
+        ba.n_loss = (float)u->batch_global * r->V; ba.loss_out = loss_out;
+    }
+    k_colstats<<<nb, CS_COLS * CS_ROWS, 0, st>>>(hp, hn, vp, vn, ea, eb, B, r->V, r->H, st_small, sq_part,
+                                                 ctx->ticket, ba);
     IMDBN_CHECK_LAUNCH(ctx, "k_colstats");
-    const int cols = std::max(r->V, r->H);
-    if (apply)
-        k_bias_update<<<(cols + 255) / 256, 256, 0, st>>>(
-            st_small, sq_part, nb, r->V, r->H, r->hb, r->hbm, r->vb, r->vbm, u->lr, u->momentum,
-            (float)u->batch_global, u->sparsity, u->sparsity_target, (float)u->batch_global * r->V,
-            loss_out, 1);
-    else
-        k_bias_update<<<1, 32, 0, st>>>(st_small, sq_part, nb, r->V, r->H, nullptr, nullptr, nullptr, nullptr,
-                                        0.f, 0.f, 1.f, 0, 0.f, 1.f, nullptr, 0);
-    IMDBN_CHECK_LAUNCH(ctx, "k_bias_update");
     return 0;
 }
 
@@ -431,6 +430,10 @@ int imdbn_ctx_create(imdbn_ctx** out, int device) {
             return -3;  // sm_100a code only
         }
     }
+    if (cudaMalloc((void**)&c->ticket, 256) != cudaSuccess || cudaMemset(c->ticket, 0, 256) != cudaSuccess) {
+        delete c;
+        return (int)cudaErrorMemoryAllocation;
+    }
     *out = c;
     return 0;
 }
@@ -439,6 +442,7 @@ void imdbn_ctx_destroy(imdbn_ctx* ctx) {
     if (!ctx) return;
     tc_destroy(ctx);
     prof_clear(ctx);
+    if (ctx->ticket) cudaFree(ctx->ticket);
     if (ctx->arena.base) cudaFree(ctx->arena.base);
     delete ctx;
 }

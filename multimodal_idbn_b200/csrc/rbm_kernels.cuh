@@ -12,6 +12,19 @@ namespace imdbn {
 __device__ __forceinline__ int finish_nslabs(const SKPlan& sk, int splits, int col) {
     return sk.k_iters ? sk_nslabs(sk, col / sk.tile_w) : splits;
 }
+// part[0*stride + i] + part[1*stride + i] + ... in slab order; the loads of 8 slabs are issued
+// together (independent), only the additions are sequential.
+__device__ __forceinline__ float sum_slabs(const float* __restrict__ part, int ns, size_t stride, size_t i) {
+    float x = 0.0f;
+    for (int s0 = 0; s0 < ns; s0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (s0 + u < ns) ? part[(size_t)(s0 + u) * stride + i] : 0.0f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if (s0 + u < ns) x += v[u];
+    }
+    return x;
+}
 
 // ---- up pass finish: p = sigmoid((sum_s part + hb)/T), s = (p > U)           rbm.py:92,175,203
 __global__ void k_finish_up(const float* __restrict__ part, int splits, SKPlan sk, int B, int H,
@@ -24,9 +37,7 @@ __global__ void k_finish_up(const float* __restrict__ part, int splits, SKPlan s
     const float bj = hb[j];
     for (int b = blockIdx.y; b < B; b += gridDim.y) {
         const size_t i = (size_t)b * H + j;
-        float x = 0.0f;
-        for (int s = 0; s < ns; ++s) x += part[(size_t)s * n + i];
-        x = add_rn(x, bj) / T;
+        float x = add_rn(sum_slabs(part, ns, n, i), bj) / T;
         const float p = sigmoidf_ref(x);
         if (p_out) p_out[i] = p;
         if (s_out) s_out[i] = (p > rf_uniform(key, draw_u, b, j)) ? 1.0f : 0.0f;
@@ -46,9 +57,7 @@ __global__ void k_finish_down(const float* __restrict__ part, int splits, SKPlan
     const float bc = vb[c];
     for (int b = blockIdx.y; b < B; b += gridDim.y) {
         const size_t i = (size_t)b * V + c;
-        float x = 0.0f;
-        for (int s = 0; s < ns; ++s) x += part[(size_t)s * n + i];
-        x = add_rn(x, bc) / T;
+        float x = add_rn(sum_slabs(part, ns, n, i), bc) / T;
         if (logits_out) logits_out[i] = x;
         const float p = sigmoidf_ref(x);
         if (p_out) p_out[i] = p;
@@ -110,11 +119,19 @@ __global__ void k_groups(const float* __restrict__ logits, float* __restrict__ p
 // Block = 32 columns x 8 row lanes; every thread sums rows y, y+8, ...; the 8 lane sums are added in
 // lane order (deterministic).  One squared-error partial per block.
 constexpr int CS_COLS = 32, CS_ROWS = 8;
+struct BiasArgs {            // apply != 0: update the biases of the block's columns in the same kernel
+    int apply;
+    float* hb; float* hbm; float* vb; float* vbm;
+    float lr, mom, bsz; int sparsity; float sp_target;
+    float n_loss; float* loss_out;
+};
 __global__ void __launch_bounds__(CS_COLS * CS_ROWS)
 k_colstats(const float* __restrict__ hp, const float* __restrict__ hn, const float* __restrict__ vp,
            const float* __restrict__ vn, const float* __restrict__ ea, const float* __restrict__ eb, int B,
-           int V, int H, float* __restrict__ out, float* __restrict__ sq_part) {
+           int V, int H, float* __restrict__ out, float* __restrict__ sq_part, unsigned int* __restrict__ ticket,
+           BiasArgs ba) {
     __shared__ float red[5][CS_ROWS][CS_COLS];
+    __shared__ unsigned int s_last;
     const int x = threadIdx.x % CS_COLS, y = threadIdx.x / CS_COLS;
     const int c = blockIdx.x * CS_COLS + x;
     float ha = 0.f, hb_ = 0.f, va = 0.f, vb_ = 0.f, sq = 0.f;
@@ -138,11 +155,45 @@ k_colstats(const float* __restrict__ hp, const float* __restrict__ hn, const flo
             for (int r = 0; r < CS_ROWS; ++r) a += red[q][r][x];
             t[q] = a;
         }
-        if (c < H) { out[c] = t[0] - t[1]; out[H + V + c] = t[0]; }
-        if (c < V) out[H + c] = t[2] - t[3];
+        if (c < H) {
+            const float dh = t[0] - t[1];
+            out[c] = dh; out[H + V + c] = t[0];
+            if (ba.apply) {                               // rbm.py:216-220 / 478-479
+                float m = add_rn(mul_rn(ba.hbm[c], ba.mom), mul_rn(ba.lr, dh) / ba.bsz);
+                if (ba.sparsity) m = add_rn(m, mul_rn(-ba.lr, add_rn(t[0] / ba.bsz, -ba.sp_target)));
+                ba.hbm[c] = m;
+                ba.hb[c] = add_rn(ba.hb[c], m);
+            }
+        }
+        if (c < V) {
+            const float dv = t[2] - t[3];
+            out[H + c] = dv;
+            if (ba.apply) {                               // rbm.py:223-224 / 480-481
+                const float m = add_rn(mul_rn(ba.vbm[c], ba.mom), mul_rn(ba.lr, dv) / ba.bsz);
+                ba.vbm[c] = m;
+                ba.vb[c] = add_rn(ba.vb[c], m);
+            }
+        }
         float s = t[4];
         for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (x == 0) sq_part[blockIdx.x] = s;
+        if (x == 0) {
+            sq_part[blockIdx.x] = s;
+            __threadfence();
+            s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+        }
+        __syncwarp();
+        // the last block to finish adds the per-block squared errors in index order (deterministic)
+        if (s_last) {
+            __threadfence();
+            float v = 0.f;
+            for (int i = x; i < (int)gridDim.x; i += 32) v += __ldcg(sq_part + i);
+            for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (x == 0) {
+                out[2 * H + V] = v;
+                if (ba.loss_out) *ba.loss_out = v / ba.n_loss;   // rbm.py:226 / 483
+                *ticket = 0u;
+            }
+        }
     }
 }
 
@@ -211,9 +262,7 @@ __global__ void k_free_energy(const float* __restrict__ part, int splits, SKPlan
     float th = 0.0f, tv = 0.0f;
     for (int j = threadIdx.x; j < H; j += blockDim.x) {
         const int ns = sk.k_iters ? sk_nslabs(sk, j / sk.tile_w) : splits;
-        float x = 0.0f;
-        for (int s = 0; s < ns; ++s) x += part[(size_t)s * n + (size_t)b * H + j];
-        x = add_rn(x, hb[j]);
+        float x = add_rn(sum_slabs(part, ns, n, (size_t)b * H + j), hb[j]);
         th += (x > 20.0f) ? x : log1pf(expf(x));   // torch softplus, threshold 20
     }
     for (int c = threadIdx.x; c < V; c += blockDim.x) tv = fmaf(v[(size_t)b * V + c], vb[c], tv);

@@ -273,7 +273,8 @@ SKPlan tc_plan(const imdbn_ctx* ctx, int M_total, int K_total) {
     const int m_tiles = (M_total + TS_BM - 1) / TS_BM;
     p.k_iters = (K_total + TS_BK - 1) / TS_BK;
     const int total = m_tiles * p.k_iters;
-    const int G = std::min(ctx->num_sms, total);
+    // at least 4 k-iterations per CTA: fewer, longer ranges for small layers (fewer slabs to add)
+    const int G = std::max(1, std::min(ctx->num_sms, total / 4));
     p.q = total / G;
     p.r = total % G;
     p.tile_w = TS_BM;
