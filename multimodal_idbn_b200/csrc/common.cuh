@@ -88,6 +88,27 @@ struct ProfScope {
     }
 };
 
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------
+// Every kernel launched through launch_pdl() begins with pdl_trigger() (its dependents may be
+// scheduled as soon as all of its CTAs have started) and executes pdl_wait() before it touches
+// global memory written by earlier kernels (blocks until those grids have completed and flushed).
+// The on-chip prologue of kernel N+1 (barrier init, TMEM allocation, descriptor prefetch, block
+// scheduling) thereby overlaps the tail of kernel N instead of following it.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Reserve `total` bytes for the current API call.  Growing synchronises the stream once (sizes
 // settle after the first calls); buffers are only valid until the next API call on this context.
 inline int arena_begin(imdbn_ctx* ctx, size_t total, cudaStream_t st) {

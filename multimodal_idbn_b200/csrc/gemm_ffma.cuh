@@ -82,6 +82,8 @@ template <bool A_KCONTIG, bool B_NCONTIG, int EPI>
 __global__ void __launch_bounds__(GTHREADS) k_gemm_ffma(GemmArgs g) {
     __shared__ __align__(16) float As[GBK][GAP];
     __shared__ __align__(16) float Bs[GBK][GBP];
+    pdl_trigger();
+    pdl_wait();
 
     const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
     const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;

@@ -64,7 +64,7 @@ int gemm_up(imdbn_ctx* ctx, const imdbn_rbm* r, const float* v, int B, const Pas
     g.M = B; g.N = r->H; g.K = r->V;
     g.k_per_split = pl.kps; g.C = part;
     dim3 grid((g.N + GBN - 1) / GBN, (g.M + GBM - 1) / GBM, pl.splits);
-    k_gemm_ffma<true, true, EPI_STORE><<<grid, GTHREADS, 0, st>>>(g);
+    IMDBN_CUDA(ctx, launch_pdl(k_gemm_ffma<true, true, EPI_STORE>, grid, dim3(GTHREADS), 0, st, g));
     IMDBN_CHECK_LAUNCH(ctx, "k_gemm_ffma(up)");
     return 0;
 }
@@ -80,7 +80,7 @@ int gemm_down(imdbn_ctx* ctx, const imdbn_rbm* r, const float* h, int B, const P
     g.M = B; g.N = r->V; g.K = r->H;
     g.k_per_split = pl.kps; g.C = part;
     dim3 grid((g.N + GBN - 1) / GBN, (g.M + GBM - 1) / GBM, pl.splits);
-    k_gemm_ffma<true, false, EPI_STORE><<<grid, GTHREADS, 0, st>>>(g);
+    IMDBN_CUDA(ctx, launch_pdl(k_gemm_ffma<true, false, EPI_STORE>, grid, dim3(GTHREADS), 0, st, g));
     IMDBN_CHECK_LAUNCH(ctx, "k_gemm_ffma(down)");
     return 0;
 }
@@ -101,12 +101,12 @@ int gemm_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* vp, const float*
     dim3 grid((g.N + GBN - 1) / GBN, (g.M + GBM - 1) / GBM, 1);
     if (dS_out) {
         g.C = dS_out;
-        k_gemm_ffma<false, true, EPI_STORE><<<grid, GTHREADS, 0, st>>>(g);
+        IMDBN_CUDA(ctx, launch_pdl(k_gemm_ffma<false, true, EPI_STORE>, grid, dim3(GTHREADS), 0, st, g));
     } else {
         g.W = r->W; g.Wm = r->Wm;
         g.lr = upd->lr; g.mom = upd->momentum; g.wd = upd->weight_decay;
         g.bsz = (float)upd->batch_global;
-        k_gemm_ffma<false, true, EPI_UPDATE><<<grid, GTHREADS, 0, st>>>(g);
+        IMDBN_CUDA(ctx, launch_pdl(k_gemm_ffma<false, true, EPI_UPDATE>, grid, dim3(GTHREADS), 0, st, g));
     }
     IMDBN_CHECK_LAUNCH(ctx, "k_gemm_ffma(stats)");
     return 0;
@@ -117,8 +117,8 @@ int up_pass(imdbn_ctx* ctx, const imdbn_rbm* r, const float* v, int B, float T, 
             cudaStream_t st) {
     int rc = gemm_up(ctx, r, v, B, pl, part, st);
     if (rc) return rc;
-    k_finish_up<<<dim3((r->H + 255) / 256, std::min(B, 16384)), 256, 0, st>>>(
-        part, pl.splits, pl.sk, B, r->H, r->hb, fmaxf(1e-6f, T), p_out, s_out, key, draw_u);
+    IMDBN_CUDA(ctx, launch_pdl(k_finish_up, dim3((r->H + 255) / 256, std::min(B, 16384)), dim3(256), 0, st,
+                               part, pl.splits, pl.sk, B, r->H, r->hb, fmaxf(1e-6f, T), p_out, s_out, key, draw_u));
     IMDBN_CHECK_LAUNCH(ctx, "k_finish_up");
     return 0;
 }
@@ -131,8 +131,8 @@ int down_pass(imdbn_ctx* ctx, const imdbn_rbm* r, const float* h, int B, float T
     if (rc) return rc;
     const Groups gr = make_groups(r);
     float* lg = logits_out ? logits_out : (gr.n ? logits_tmp : nullptr);
-    k_finish_down<<<dim3((r->V + 255) / 256, std::min(B, 16384)), 256, 0, st>>>(
-        part, pl.splits, pl.sk, B, r->V, r->vb, fmaxf(1e-6f, T), p_out, lg, s_out, key, draw_u);
+    IMDBN_CUDA(ctx, launch_pdl(k_finish_down, dim3((r->V + 255) / 256, std::min(B, 16384)), dim3(256), 0, st,
+                               part, pl.splits, pl.sk, B, r->V, r->vb, fmaxf(1e-6f, T), p_out, lg, s_out, key, draw_u));
     IMDBN_CHECK_LAUNCH(ctx, "k_finish_down");
     if (gr.n && (p_out || s_out)) {
         // the groups need a probability buffer even when the caller only wants samples
@@ -173,8 +173,8 @@ int finish_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* hp, const floa
         ba.sparsity = u->sparsity; ba.sp_target = u->sparsity_target;
         ba.n_loss = (float)u->batch_global * r->V; ba.loss_out = loss_out;
     }
-    k_colstats<<<nb, CS_COLS * CS_ROWS, 0, st>>>(hp, hn, vp, vn, ea, eb, B, r->V, r->H, st_small, sq_part,
-                                                 ctx->ticket, ba);
+    IMDBN_CUDA(ctx, launch_pdl(k_colstats, dim3(nb), dim3(CS_COLS * CS_ROWS), 0, st, hp, hn, vp, vn, ea, eb, B,
+                               r->V, r->H, st_small, sq_part, ctx->ticket, ba));
     IMDBN_CHECK_LAUNCH(ctx, "k_colstats");
     return 0;
 }

@@ -30,6 +30,8 @@ __device__ __forceinline__ float sum_slabs(const float* __restrict__ part, int n
 __global__ void k_finish_up(const float* __restrict__ part, int splits, SKPlan sk, int B, int H,
                             const float* __restrict__ hb, float T, float* __restrict__ p_out,
                             float* __restrict__ s_out, RngKey key, uint32_t draw_u) {
+    pdl_trigger();
+    pdl_wait();
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= H) return;
     const int ns = finish_nslabs(sk, splits, j);
@@ -50,6 +52,8 @@ __global__ void k_finish_down(const float* __restrict__ part, int splits, SKPlan
                               const float* __restrict__ vb, float T, float* __restrict__ p_out,
                               float* __restrict__ logits_out, float* __restrict__ s_out,
                               RngKey key, uint32_t draw_u) {
+    pdl_trigger();
+    pdl_wait();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= V) return;
     const int ns = finish_nslabs(sk, splits, c);
@@ -82,6 +86,8 @@ __global__ void k_bernoulli(const float* __restrict__ p, int B, int V, float* __
 // With logits == nullptr the probabilities already in p are used (sample_visible on a given p).
 __global__ void k_groups(const float* __restrict__ logits, float* __restrict__ p, float* __restrict__ s_out,
                          int B, int V, Groups gr, RngKey key, uint32_t draw_cat) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (warp >= B * gr.n) return;
@@ -132,6 +138,8 @@ k_colstats(const float* __restrict__ hp, const float* __restrict__ hn, const flo
            BiasArgs ba) {
     __shared__ float red[5][CS_ROWS][CS_COLS];
     __shared__ unsigned int s_last;
+    pdl_trigger();
+    pdl_wait();
     const int x = threadIdx.x % CS_COLS, y = threadIdx.x / CS_COLS;
     const int c = blockIdx.x * CS_COLS + x;
     float ha = 0.f, hb_ = 0.f, va = 0.f, vb_ = 0.f, sq = 0.f;

@@ -134,6 +134,7 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int beg = sk_beg(a.sk, cta), end = sk_beg(a.sk, cta + 1);
     const int k_iters = a.sk.k_iters;
 
+    pdl_trigger();
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
@@ -146,6 +147,7 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                 // everything above overlapped the previous kernel's tail
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -298,7 +300,7 @@ static int launch_stream(imdbn_ctx* ctx, const CUtensorMap* tmA, const CUtensorM
                          cudaStream_t st) {
     const size_t smem = (size_t)a.stages * ts_stage_bytes(a.Npad) + 1024 + 256;
     IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_tc_stream<A_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_tc_stream<A_MN><<<G, TS_THREADS, smem, st>>>(*tmA, *tmB, a);
+    IMDBN_CUDA(ctx, launch_pdl(k_tc_stream<A_MN>, dim3(G), dim3(TS_THREADS), smem, st, *tmA, *tmB, a));
     IMDBN_CHECK_LAUNCH(ctx, "k_tc_stream");
     return 0;
 }
@@ -351,10 +353,10 @@ int tc_gemm_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* vp, const flo
     const int G = std::min(ctx->num_sms, a.m_tiles * a.n_tiles);
     if (dS_out) {
         IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_tc_stats<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
-        k_tc_stats<false><<<G, ST_THREADS, ST_SMEM, st>>>(*tVP, *tVN, *tHP, *tHN, *tW, *tWm, a);
+        IMDBN_CUDA(ctx, launch_pdl(k_tc_stats<false>, dim3(G), dim3(ST_THREADS), ST_SMEM, st, *tVP, *tVN, *tHP, *tHN, *tW, *tWm, a));
     } else {
         IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_tc_stats<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
-        k_tc_stats<true><<<G, ST_THREADS, ST_SMEM, st>>>(*tVP, *tVN, *tHP, *tHN, *tW, *tWm, a);
+        IMDBN_CUDA(ctx, launch_pdl(k_tc_stats<true>, dim3(G), dim3(ST_THREADS), ST_SMEM, st, *tVP, *tVN, *tHP, *tHN, *tW, *tWm, a));
     }
     IMDBN_CHECK_LAUNCH(ctx, "k_tc_stats");
     return 0;

@@ -65,6 +65,7 @@ k_tc_stats(const __grid_constant__ CUtensorMap tmVP, const __grid_constant__ CUt
     // (row-buffer locality) instead of 512-byte fragments.
     const int t_beg = blockIdx.x, t_end = n_tiles_total, t_step = gridDim.x;
 
+    pdl_trigger();
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmVP); tma_prefetch_desc(&tmVN); tma_prefetch_desc(&tmHP); tma_prefetch_desc(&tmHN);
         tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmWm);
@@ -82,6 +83,7 @@ k_tc_stats(const __grid_constant__ CUtensorMap tmVP, const __grid_constant__ CUt
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                 // everything above overlapped the previous kernel's tail
 
     if (warp == 0) {
         // ===================== operand producer =====================
