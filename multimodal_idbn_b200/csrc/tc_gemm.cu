@@ -112,6 +112,7 @@ struct StreamArgs {
     float* part;                           // [slab][B][M_total]
     uint32_t tmem_cols;
     int stages;
+    uint64_t w_policy;                     // L2 eviction priority of the W stream
 };
 
 __host__ __device__ inline int ts_stage_bytes(int Npad) { return TS_A_BYTES + Npad * TS_BK * 4; }
@@ -163,11 +164,11 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 if (A_MN) {          // W[k rows, 32 features] boxes: one per 32-feature column block
 #pragma unroll
                     for (int cb = 0; cb < TS_BM / 32; ++cb)
-                        tma_load_2d(sA + cb * (TS_BK * 128), &tmA, m0 + cb * 32, k0, &full[stage]);
+                        tma_load_2d_hint(sA + cb * (TS_BK * 128), &tmA, m0 + cb * 32, k0, &full[stage], a.w_policy);
                 } else {             // W[128 feature rows, 32 k] boxes: one per 32-wide k block
 #pragma unroll
                     for (int j = 0; j < TS_BK / 32; ++j)
-                        tma_load_2d(sA + j * (TS_BM * 128), &tmA, k0 + j * 32, m0, &full[stage]);
+                        tma_load_2d_hint(sA + j * (TS_BM * 128), &tmA, k0 + j * 32, m0, &full[stage], a.w_policy);
                 }
 #pragma unroll
                 for (int j = 0; j < TS_BK / 32; ++j)
@@ -253,6 +254,15 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+// IMDBN_L2_W / IMDBN_L2_WM = normal | first | last : experiment switch for the L2 policies
+static inline uint64_t l2_policy_env(const char* name, uint64_t dflt) {
+    const char* e = getenv(name);
+    if (!e) return dflt;
+    if (!strcmp(e, "normal")) return L2_EVICT_NORMAL;
+    if (!strcmp(e, "first")) return L2_EVICT_FIRST;
+    if (!strcmp(e, "last")) return L2_EVICT_LAST;
+    return dflt;
+}
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static inline int npad_of(int B) { return std::max(16, (B + 15) / 16 * 16); }
 static inline uint32_t pow2_cols(int n) { uint32_t c = 32; while ((int)c < n) c <<= 1; return c; }
@@ -315,6 +325,7 @@ static int stream_pass(imdbn_ctx* ctx, const imdbn_rbm* r, const float* act, int
     a.total_iters = ((M_total + TS_BM - 1) / TS_BM) * a.sk.k_iters;
     a.part = part;
     a.tmem_cols = pow2_cols(2 * a.Npad);
+    a.w_policy = l2_policy_env("IMDBN_L2_W", L2_EVICT_NORMAL);
     a.stages = std::max(2, std::min(TS_STAGES, (200 * 1024) / ts_stage_bytes(a.Npad)));
     const int G = tc_plan_ctas(a.sk, M_total);
     // W is [V, H] row-major: inner = H.  up: boxes [64 k-rows x 32 h]; down: boxes [128 v-rows x 32 h]
@@ -343,6 +354,8 @@ int tc_gemm_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* vp, const flo
     a.k_chunks = (B + ST_KC - 1) / ST_KC;
     if (upd) { a.lr = upd->lr; a.mom = upd->momentum; a.wd = upd->weight_decay; a.bsz = (float)upd->batch_global; }
     a.dbg = 0;
+    a.w_policy = l2_policy_env("IMDBN_L2_W", L2_EVICT_NORMAL);
+    a.wm_policy = l2_policy_env("IMDBN_L2_WM", L2_EVICT_NORMAL);
     const CUtensorMap* tVP = get_map(ctx, vp, r->V, B, ST_KC, true);
     const CUtensorMap* tVN = get_map(ctx, vn, r->V, B, ST_KC, true);
     const CUtensorMap* tHP = get_map(ctx, hp, r->H, B, ST_KC, true);

@@ -63,6 +63,28 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, in
         : "memory");
 }
 
+// L2 eviction-priority policies (the encodings CUTLASS passes as TMA::CacheHintSm90): used to keep the
+// weight matrix W (60 MB, re-read by every pass of a CD step) resident in the 126 MB L2 while the
+// momentum matrix W_m (touched once per step) streams through.
+constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull;
+constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;
+constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const void* tmap, int c0, int c1, uint64_t* bar,
+                                                 uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+          "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_hint(const void* tmap, int c0, int c1, const void* smem_src,
+                                                  uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+                 ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "l"(policy)
+                 : "memory");
+}
+
 // 2-D tiled store shared -> global (bulk async-group completion); out-of-bounds parts are clipped.
 __device__ __forceinline__ void tma_store_2d(const void* tmap, int c0, int c1, const void* smem_src) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"

@@ -36,6 +36,7 @@ struct StatsArgs {
     int V, H, B;
     int m_tiles, n_tiles, k_chunks;
     float lr, mom, wd, bsz;
+    uint64_t w_policy, wm_policy;   // L2 eviction priorities of the W and W_m streams
     int dbg;    // experiment switch (IMDBN_DEBUG_STATS): 1 = no operands/MMA, 2 = no W/W_m traffic
 };
 
@@ -154,8 +155,8 @@ k_tc_stats(const __grid_constant__ CUtensorMap tmVP, const __grid_constant__ CUt
                     uint8_t* slot = slots + s * ST_SLOT_BYTES;
                     mbar_wait(&io_empty[s], ((hh / ST_NSLOT) & 1) ^ 1);
                     mbar_expect_tx(&io_full[s], ST_SLOT_BYTES);
-                    tma_load_2d(slot, &tmW, n0 + qt * 32, m0, &io_full[s]);
-                    tma_load_2d(slot + ST_IO_BOX, &tmWm, n0 + qt * 32, m0, &io_full[s]);
+                    tma_load_2d_hint(slot, &tmW, n0 + qt * 32, m0, &io_full[s], a.w_policy);
+                    tma_load_2d_hint(slot + ST_IO_BOX, &tmWm, n0 + qt * 32, m0, &io_full[s], a.wm_policy);
                 }
             }
         }
@@ -170,8 +171,8 @@ k_tc_stats(const __grid_constant__ CUtensorMap tmVP, const __grid_constant__ CUt
                     const uint8_t* slot = slots + s * ST_SLOT_BYTES;
                     mbar_wait(&io_written[s], (hh / ST_NSLOT) & 1);
                     if (a.dbg != 3) {
-                        tma_store_2d(&tmW, n0 + qt * 32, m0, slot);
-                        if (UPDATE) tma_store_2d(&tmWm, n0 + qt * 32, m0, slot + ST_IO_BOX);
+                        tma_store_2d_hint(&tmW, n0 + qt * 32, m0, slot, UPDATE ? a.w_policy : L2_EVICT_NORMAL);
+                        if (UPDATE) tma_store_2d_hint(&tmWm, n0 + qt * 32, m0, slot + ST_IO_BOX, a.wm_policy);
                     }
                     tma_store_commit();
                     tma_store_wait_read();            // shared memory of the slot may be overwritten

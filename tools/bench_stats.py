@@ -6,7 +6,7 @@ import multimodal_idbn_b200 as M
 from multimodal_idbn_b200 import _lib as L
 M.set_precision(os.environ.get("PREC", "tf32"))
 dev = "cuda"
-V, H, B = 10000, 1500, 64
+V, H, B = 10000, int(os.environ.get("HID", "1500")), 64
 r = M.RBM(V, H, 0.1, 1e-4, 0.5).to(dev)
 x = (torch.rand(B, V, device=dev) < 0.1).float()
 ctx, st = L.context_for(x)
