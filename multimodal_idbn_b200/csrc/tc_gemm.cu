@@ -132,6 +132,7 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cta = blockIdx.x;
+    const int b0 = blockIdx.y * a.Npad;          // batches wider than 256 rows: one 256-row chunk per blockIdx.y
     const int beg = sk_beg(a.sk, cta), end = sk_beg(a.sk, cta + 1);
     const int k_iters = a.sk.k_iters;
 
@@ -172,7 +173,7 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 }
 #pragma unroll
                 for (int j = 0; j < TS_BK / 32; ++j)
-                    tma_load_2d(sB + j * (a.Npad * 128), &tmB, k0 + j * 32, 0, &full[stage]);
+                    tma_load_2d(sB + j * (a.Npad * 128), &tmB, k0 + j * 32, b0, &full[stage]);
                 if (++stage == a.stages) { stage = 0; phase ^= 1; }
             }
         }
@@ -223,7 +224,7 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             mbar_wait(&acc_full[buf], (seg >> 1) & 1);
             tc_fence_after();
             const int m = tile * TS_BM + quad * 32 + lane;
-            float* dst = a.part + (size_t)slab * a.B * a.M_total + m;
+            float* dst = a.part + ((size_t)slab * a.B + b0) * a.M_total + m;
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * a.Npad);
             for (int c0 = 0; c0 < a.Npad; c0 += 16) {
                 float v[16];
@@ -231,7 +232,7 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 if (m < a.M_total) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
-                        if (c0 + i < a.B) dst[(size_t)(c0 + i) * a.M_total] = v[i];
+                        if (b0 + c0 + i < a.B) dst[(size_t)(c0 + i) * a.M_total] = v[i];
                 }
             }
             tc_fence_before();
@@ -272,7 +273,7 @@ bool tc_shape_ok(const imdbn_rbm* r, int B) {
 }
 
 bool tc_up_supported(const imdbn_ctx* ctx, const imdbn_rbm* r, int B) {
-    return tc_shape_ok(r, B) && B <= 256 && tc_state(const_cast<imdbn_ctx*>(ctx))->encode != nullptr;
+    return tc_shape_ok(r, B) && tc_state(const_cast<imdbn_ctx*>(ctx))->encode != nullptr;
 }
 bool tc_down_supported(const imdbn_ctx* ctx, const imdbn_rbm* r, int B) { return tc_up_supported(ctx, r, B); }
 bool tc_stats_supported(const imdbn_ctx* ctx, const imdbn_rbm* r, int B) {
@@ -307,10 +308,10 @@ int tc_plan_max_slabs(const SKPlan& p, int M_total) {
 
 template <bool A_MN>
 static int launch_stream(imdbn_ctx* ctx, const CUtensorMap* tmA, const CUtensorMap* tmB, StreamArgs& a, int G,
-                         cudaStream_t st) {
+                         int chunks, cudaStream_t st) {
     const size_t smem = (size_t)a.stages * ts_stage_bytes(a.Npad) + 1024 + 256;
     IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_tc_stream<A_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    IMDBN_CUDA(ctx, launch_pdl(k_tc_stream<A_MN>, dim3(G), dim3(TS_THREADS), smem, st, *tmA, *tmB, a));
+    IMDBN_CUDA(ctx, launch_pdl(k_tc_stream<A_MN>, dim3(G, chunks), dim3(TS_THREADS), smem, st, *tmA, *tmB, a));
     IMDBN_CHECK_LAUNCH(ctx, "k_tc_stream");
     return 0;
 }
@@ -320,7 +321,8 @@ static int stream_pass(imdbn_ctx* ctx, const imdbn_rbm* r, const float* act, int
     const int M_total = up ? r->H : r->V, K_total = up ? r->V : r->H;
     if (!aligned16(act)) return fail(ctx, -1, "tc pass: activation pointer must be 16-byte aligned");
     StreamArgs a{};
-    a.M_total = M_total; a.K_total = K_total; a.B = B; a.Npad = npad_of(B);
+    a.M_total = M_total; a.K_total = K_total; a.B = B; a.Npad = B > 256 ? 256 : npad_of(B);
+    const int chunks = (B + a.Npad - 1) / a.Npad;
     a.sk = tc_plan(ctx, M_total, K_total);
     a.total_iters = ((M_total + TS_BM - 1) / TS_BM) * a.sk.k_iters;
     a.part = part;
@@ -332,7 +334,8 @@ static int stream_pass(imdbn_ctx* ctx, const imdbn_rbm* r, const float* act, int
     const CUtensorMap* tmA = get_map(ctx, r->W, r->H, r->V, up ? TS_BK : TS_BM, up);
     const CUtensorMap* tmB = get_map(ctx, act, K_total, B, a.Npad, false);
     if (!tmA || !tmB) return fail(ctx, -5, "cuTensorMapEncodeTiled failed");
-    return up ? launch_stream<true>(ctx, tmA, tmB, a, G, st) : launch_stream<false>(ctx, tmA, tmB, a, G, st);
+    return up ? launch_stream<true>(ctx, tmA, tmB, a, G, chunks, st)
+              : launch_stream<false>(ctx, tmA, tmB, a, G, chunks, st);
 }
 
 int tc_gemm_up(imdbn_ctx* ctx, const imdbn_rbm* r, const float* v, int B, float* part, cudaStream_t st) {

@@ -39,7 +39,7 @@ SHAPES = [(10000, 1500), (1500, 500), (532, 256), (128, 128), (36, 20)]
 
 
 @pytest.mark.parametrize("V,H", SHAPES)
-@pytest.mark.parametrize("B", [1, 64, 130, 256])
+@pytest.mark.parametrize("B", [1, 64, 130, 256, 700])
 def test_up_down_tf32_vs_oracle(M, V, H, B):
     st, r = make(M, V, H, seed=V + H)
     gen = torch.Generator().manual_seed(B)
