@@ -27,6 +27,44 @@ struct ChainArgs {
     int Vp, Hp;   // padded (multiple of 4) smem row lengths
 };
 
+// acc[r] += sum_k x[r][k] * w[k*ld]  (k sequential: the summation order of a plain dot product).
+// 16 weight loads are in flight per thread: at small batch this loop is bound by L2 latency.
+template <int R>
+__device__ __forceinline__ void chain_dot(const float* __restrict__ wcol, int ld, int K, int Kp,
+                                          const float* __restrict__ xs, float (&acc)[R]) {
+    constexpr int KU = 16;
+    int k = 0;
+    for (; k + KU <= Kp; k += KU) {
+        float w[KU];
+#pragma unroll
+        for (int q = 0; q < KU; ++q) w[q] = (k + q < K) ? __ldg(wcol + (size_t)(k + q) * ld) : 0.0f;
+#pragma unroll
+        for (int q4 = 0; q4 < KU; q4 += 4) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float4 x = *reinterpret_cast<const float4*>(xs + r * Kp + k + q4);
+                acc[r] = fmaf(x.x, w[q4 + 0], acc[r]);
+                acc[r] = fmaf(x.y, w[q4 + 1], acc[r]);
+                acc[r] = fmaf(x.z, w[q4 + 2], acc[r]);
+                acc[r] = fmaf(x.w, w[q4 + 3], acc[r]);
+            }
+        }
+    }
+    for (; k < Kp; k += 4) {
+        float w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) w[q] = (k + q < K) ? __ldg(wcol + (size_t)(k + q) * ld) : 0.0f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float4 x = *reinterpret_cast<const float4*>(xs + r * Kp + k);
+            acc[r] = fmaf(x.x, w[0], acc[r]);
+            acc[r] = fmaf(x.y, w[1], acc[r]);
+            acc[r] = fmaf(x.z, w[2], acc[r]);
+            acc[r] = fmaf(x.w, w[3], acc[r]);
+        }
+    }
+}
+
 template <int R>
 __global__ void __launch_bounds__(CHAIN_THREADS) k_chain(ChainArgs a) {
     extern __shared__ __align__(16) float smem[];
@@ -74,20 +112,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain(ChainArgs a) {
             float acc[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) acc[r] = 0.0f;
-            const float* wcol = a.W + j;
-            for (int k = 0; k < a.Vp; k += 4) {
-                float w[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) w[q] = (k + q < a.V) ? __ldg(wcol + (size_t)(k + q) * a.H) : 0.0f;
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const float4 x = *reinterpret_cast<const float4*>(vs + r * a.Vp + k);
-                    acc[r] = fmaf(x.x, w[0], acc[r]);
-                    acc[r] = fmaf(x.y, w[1], acc[r]);
-                    acc[r] = fmaf(x.z, w[2], acc[r]);
-                    acc[r] = fmaf(x.w, w[3], acc[r]);
-                }
-            }
+            chain_dot<R>(a.W + j, a.H, a.V, a.Vp, vs, acc);
             const float bj = a.hb[j];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
@@ -107,20 +132,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain(ChainArgs a) {
             float acc[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) acc[r] = 0.0f;
-            const float* wcol = a.Wt + c;
-            for (int k = 0; k < a.Hp; k += 4) {
-                float w[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) w[q] = (k + q < a.H) ? __ldg(wcol + (size_t)(k + q) * a.V) : 0.0f;
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const float4 x = *reinterpret_cast<const float4*>(hs + r * a.Hp + k);
-                    acc[r] = fmaf(x.x, w[0], acc[r]);
-                    acc[r] = fmaf(x.y, w[1], acc[r]);
-                    acc[r] = fmaf(x.z, w[2], acc[r]);
-                    acc[r] = fmaf(x.w, w[3], acc[r]);
-                }
-            }
+            chain_dot<R>(a.Wt + c, a.V, a.H, a.Hp, hs, acc);
             const float bc = a.vb[c];
 #pragma unroll
             for (int r = 0; r < R; ++r) {

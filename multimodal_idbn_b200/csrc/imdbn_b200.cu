@@ -8,6 +8,8 @@
 #include "gemm_ffma.cuh"
 #include "rbm_kernels.cuh"
 #include "chain_kernel.cuh"
+#include "chain_stepped.cuh"
+#include "finish_vec.cuh"
 #include "tc_gemm.cuh"
 
 using namespace imdbn;
@@ -112,13 +114,31 @@ int gemm_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* vp, const float*
     return 0;
 }
 
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+// the float4 finishes need N % 4 == 0, 16-byte aligned rows / outputs and a 32-bit quad index
+inline bool vec_ok(int B, int N, const float* bias, const float* a, const float* b, const float* c) {
+    return (N % 4) == 0 && al16(bias) && al16(a) && al16(b) && al16(c) && (size_t)B * (N / 4) < 0x7fffffffull;
+}
+
 int up_pass(imdbn_ctx* ctx, const imdbn_rbm* r, const float* v, int B, float T, float* p_out,
             float* s_out, const RngKey& key, uint32_t draw_u, const PassPlan& pl, float* part,
             cudaStream_t st) {
     int rc = gemm_up(ctx, r, v, B, pl, part, st);
     if (rc) return rc;
-    IMDBN_CUDA(ctx, launch_pdl(k_finish_up, dim3((r->H + 255) / 256, std::min(B, 16384)), dim3(256), 0, st,
-                               part, pl.splits, pl.sk, B, r->H, r->hb, fmaxf(1e-6f, T), p_out, s_out, key, draw_u));
+    if (vec_ok(B, r->H, r->hb, p_out, s_out, nullptr)) {
+        const size_t quads = (size_t)B * (r->H / 4);
+        if (ctx->precision == IMDBN_PREC_TF32)
+            IMDBN_CUDA(ctx, launch_pdl(k_finish_up4<true>, dim3(vec_blocks(quads, ctx->num_sms)), dim3(256), 0, st,
+                                       part, pl.splits, pl.sk, B, r->H, r->hb, fmaxf(1e-6f, T), 0.0f, p_out, s_out,
+                                       key, draw_u, 0u));
+        else
+            IMDBN_CUDA(ctx, launch_pdl(k_finish_up4<false>, dim3(vec_blocks(quads, ctx->num_sms)), dim3(256), 0, st,
+                                       part, pl.splits, pl.sk, B, r->H, r->hb, fmaxf(1e-6f, T), 0.0f, p_out, s_out,
+                                       key, draw_u, 0u));
+    } else {
+        IMDBN_CUDA(ctx, launch_pdl(k_finish_up, dim3((r->H + 255) / 256, std::min(B, 16384)), dim3(256), 0, st,
+                                   part, pl.splits, pl.sk, B, r->H, r->hb, fmaxf(1e-6f, T), p_out, s_out, key, draw_u));
+    }
     IMDBN_CHECK_LAUNCH(ctx, "k_finish_up");
     return 0;
 }
@@ -131,8 +151,21 @@ int down_pass(imdbn_ctx* ctx, const imdbn_rbm* r, const float* h, int B, float T
     if (rc) return rc;
     const Groups gr = make_groups(r);
     float* lg = logits_out ? logits_out : (gr.n ? logits_tmp : nullptr);
-    IMDBN_CUDA(ctx, launch_pdl(k_finish_down, dim3((r->V + 255) / 256, std::min(B, 16384)), dim3(256), 0, st,
-                               part, pl.splits, pl.sk, B, r->V, r->vb, fmaxf(1e-6f, T), p_out, lg, s_out, key, draw_u));
+    if (vec_ok(B, r->V, r->vb, p_out, s_out, lg)) {
+        const size_t quads = (size_t)B * (r->V / 4);
+        ChainPost4 cp{};
+        if (ctx->precision == IMDBN_PREC_TF32)
+            IMDBN_CUDA(ctx, launch_pdl(k_finish_down4<true>, dim3(vec_blocks(quads, ctx->num_sms)), dim3(256), 0, st,
+                                       part, pl.splits, pl.sk, B, r->V, r->vb, fmaxf(1e-6f, T), 0.0f, p_out, lg, s_out,
+                                       key, draw_u, 0u, cp));
+        else
+            IMDBN_CUDA(ctx, launch_pdl(k_finish_down4<false>, dim3(vec_blocks(quads, ctx->num_sms)), dim3(256), 0, st,
+                                       part, pl.splits, pl.sk, B, r->V, r->vb, fmaxf(1e-6f, T), 0.0f, p_out, lg, s_out,
+                                       key, draw_u, 0u, cp));
+    } else {
+        IMDBN_CUDA(ctx, launch_pdl(k_finish_down, dim3((r->V + 255) / 256, std::min(B, 16384)), dim3(256), 0, st,
+                                   part, pl.splits, pl.sk, B, r->V, r->vb, fmaxf(1e-6f, T), p_out, lg, s_out, key, draw_u));
+    }
     IMDBN_CHECK_LAUNCH(ctx, "k_finish_down");
     if (gr.n && (p_out || s_out)) {
         // the groups need a probability buffer even when the caller only wants samples
@@ -202,8 +235,81 @@ int launch_chain_r(imdbn_ctx* ctx, const ChainArgs& a, size_t smem, cudaStream_t
     return 0;
 }
 
-size_t chain_ws_floats(const imdbn_rbm* r, int n_steps) {
-    return (size_t)r->V * r->H + 3 * (size_t)std::max(1, n_steps) + 256;
+// Large mean-field batches in tf32 mode run the chain step by step on the tensor-core passes
+// (chain_stepped.cuh); everything else uses the persistent kernel.
+bool chain_is_stepped(const imdbn_ctx* ctx, const imdbn_rbm* r, const imdbn_chain* ch, int B) {
+    return ctx->precision == IMDBN_PREC_TF32 && B >= 512 && !ch->sample_h && !ch->sample_v &&
+           tc_up_supported(ctx, r, B) && tc_down_supported(ctx, r, B);
+}
+
+size_t chain_ws_floats(const imdbn_ctx* ctx, const imdbn_rbm* r, const imdbn_chain* ch, int B) {
+    size_t n = (size_t)r->V * r->H + 3 * (size_t)std::max(1, ch->n_steps) + 256;
+    if (chain_is_stepped(ctx, r, ch, B)) {
+        const PassPlan pu = plan_pass(ctx, r, B, true), pd = plan_pass(ctx, r, B, false);
+        n += std::max(pu.part_floats, pd.part_floats) + (size_t)B * r->H + 2 * (size_t)B * r->V + 1024;
+    }
+    return n;
+}
+
+int run_chain_stepped(imdbn_ctx* ctx, const imdbn_rbm* r, const imdbn_chain* ch, int B, float* v_out,
+                      float* vprob_out, const RngKey& key, cudaStream_t st) {
+    const int V = r->V, H = r->H, n = ch->n_steps;
+    const bool noisy = ch->kind == IMDBN_CHAIN_NOISY_MF;
+    IMDBN_ARG(ctx, !noisy || n == 0 || (ch->T && ch->sigma));
+    const PassPlan pu = plan_pass(ctx, r, B, true), pd = plan_pass(ctx, r, B, false);
+    float* part = arena_take<float>(ctx, std::max(pu.part_floats, pd.part_floats));
+    float* h = arena_take<float>(ctx, (size_t)B * H);
+    float* lg = arena_take<float>(ctx, (size_t)B * V);
+    float* v = v_out;                                   // the state lives in the output buffer
+    const dim3 gv((V + 255) / 256, std::min(B, 16384)), gh((H + 255) / 256, std::min(B, 16384));
+    IMDBN_CUDA(ctx, launch_pdl(k_chain_init, gv, dim3(256), 0, st, ch->v_known, ch->known_mask, ch->v_init,
+                               B, V, key, ch->draw0, v));
+    ctx->launches++;
+    const Groups gr = make_groups(r);
+    bool vec = vec_ok(B, V, r->vb, v, ch->v_known, ch->known_mask) && vec_ok(B, H, r->hb, h, lg, vprob_out) &&
+               (ch->Dz % 4) == 0;
+    for (int g = 0; g < gr.n; ++g) vec = vec && (gr.s[g] % 4) == 0 && (gr.e[g] % 4) == 0;
+    const int total = n + (ch->final_free_sweep ? 1 : 0);
+    for (int t = 0; t < total; ++t) {
+        const bool free_sweep = (t == n);
+        const float T = (noisy && !free_sweep) ? fmaxf(1e-6f, ch->T[t]) : 1.0f;
+        const float sig = (noisy && !free_sweep) ? ch->sigma[t] : 0.0f;
+        const uint32_t d_h = ch->draw0 + 1 + (noisy ? 2 : 3) * t, d_v = d_h + 1;
+        int rc = gemm_up(ctx, r, v, B, pu, part, st);                                 // rbm.py:344 / 394
+        if (rc) return rc;
+        if (vec)
+            IMDBN_CUDA(ctx, launch_pdl(k_finish_up4<true>, dim3(vec_blocks((size_t)B * (H / 4), ctx->num_sms)), dim3(256),
+                                       0, st, part, pu.splits, pu.sk, B, H, r->hb, T, sig, h, (float*)nullptr, key, 0u, d_h));
+        else
+            IMDBN_CUDA(ctx, launch_pdl(k_chain_up_finish, gh, dim3(256), 0, st, part, pu.splits, pu.sk, B, H, r->hb,
+                                       T, sig, key, d_h, h));
+        ctx->launches++;
+        rc = gemm_down(ctx, r, h, B, pd, part, st);                                   // rbm.py:350 / 396
+        if (rc) return rc;
+        ChainPost po{};
+        po.vk = ch->v_known; po.km = ch->known_mask;
+        po.mu = (noisy && !free_sweep) ? ch->mu : nullptr; po.Dz = ch->Dz;
+        po.eta = (noisy && ch->eta && !free_sweep) ? ch->eta[t] : 0.0f;
+        po.free_sweep = free_sweep ? 1 : 0;
+        po.vprob_out = (t == total - 1) ? vprob_out : nullptr;
+        po.gr = gr;
+        if (vec) {
+            ChainPost4 cp{}; cp.enabled = 1; cp.po = po;
+            IMDBN_CUDA(ctx, launch_pdl(k_finish_down4<true>, dim3(vec_blocks((size_t)B * (V / 4), ctx->num_sms)), dim3(256),
+                                       0, st, part, pd.splits, pd.sk, B, V, r->vb, T, sig, v, lg, (float*)nullptr, key, 0u,
+                                       d_v, cp));
+        } else {
+            IMDBN_CUDA(ctx, launch_pdl(k_chain_down_finish, gv, dim3(256), 0, st, part, pd.splits, pd.sk, B, V, r->vb,
+                                       T, sig, key, d_v, po, lg, v));
+        }
+        ctx->launches++;
+        if (gr.n) {
+            IMDBN_CUDA(ctx, launch_pdl(k_chain_groups, dim3((B * gr.n * 32 + 127) / 128), dim3(128), 0, st, lg, B,
+                                       V, po, v));
+            ctx->launches++;
+        }
+    }
+    return 0;
 }
 
 // Wt / tables must come from the arena of the current call.
@@ -211,6 +317,7 @@ int run_chain(imdbn_ctx* ctx, const imdbn_rbm* r, const imdbn_chain* ch, int B, 
               float* vprob_out, const RngKey& key, float* Wt, float* tables, cudaStream_t st) {
     IMDBN_ARG(ctx, ch->n_steps >= 0 && ch->n_steps <= CHAIN_MAX_STEPS);
     IMDBN_ARG(ctx, ch->v_known && ch->known_mask);
+    if (chain_is_stepped(ctx, r, ch, B)) return run_chain_stepped(ctx, r, ch, B, v_out, vprob_out, key, st);
     ChainArgs a{};
     a.W = r->W; a.Wt = Wt; a.hb = r->hb; a.vb = r->vb;
     a.V = r->V; a.H = r->H; a.B = B;
@@ -311,9 +418,13 @@ int clamped_core(imdbn_ctx* ctx, const imdbn_rbm* r, const float* v_known, const
     const PassPlan pu = plan_pass(ctx, r, B, true), pd = plan_pass(ctx, r, B, false);
     const size_t nBH = (size_t)B * H, nBV = (size_t)B * V;
     const int nb_sq = colstat_blocks(r);
+    imdbn_chain chq{};                       // only what the workspace sizing looks at
+    chq.n_steps = n;
+    chq.sample_h = cfg->use_noisy_init ? 0 : cfg->sample_h;
+    chq.sample_v = cfg->use_noisy_init ? 0 : cfg->sample_v;
     size_t bytes = pad256(std::max(pu.part_floats, pd.part_floats)) + 3 * pad256(nBH) +
                    5 * pad256(nBV) + pad256(2 * H + V + 1) + pad256(nb_sq) +
-                   pad256(chain_ws_floats(r, n)) + 1024 + tc_ws_bytes(ctx, r, B);
+                   pad256(chain_ws_floats(ctx, r, &chq, B)) + 4096 + tc_ws_bytes(ctx, r, B);
     rc = arena_begin(ctx, bytes, st);
     if (rc) return rc;
     float* part = arena_take<float>(ctx, std::max(pu.part_floats, pd.part_floats));
@@ -599,7 +710,7 @@ int imdbn_run_chain(imdbn_ctx* ctx, const imdbn_rbm* rbm, const imdbn_chain* ch,
     int rc = check_rbm(ctx, rbm, false);
     if (rc) return rc;
     IMDBN_ARG(ctx, ch && v_out && rng && B > 0);
-    rc = arena_begin(ctx, pad256(chain_ws_floats(rbm, ch->n_steps)) + 1024, st);
+    rc = arena_begin(ctx, pad256(chain_ws_floats(ctx, rbm, ch, B)) + 4096, st);
     if (rc) return rc;
     float* Wt = arena_take<float>(ctx, (size_t)rbm->V * rbm->H);
     float* tables = arena_take<float>(ctx, 3 * (size_t)std::max(1, ch->n_steps));

@@ -113,3 +113,25 @@ def test_tf32_and_fp32_modes_agree_on_a_training_run(M):
     M.set_precision("tf32")
     assert losses["tf32"][-1] < losses["tf32"][0]
     torch.testing.assert_close(losses["tf32"], losses["fp32"], rtol=2e-2, atol=1e-3)
+
+
+def test_large_batch_chains_on_tensor_cores(M):
+    """B >= 512 mean-field chains run step by step on the tcgen05 passes (chain_stepped.cuh)."""
+    V, H, Dz, K, B = 532, 256, 500, 32, 600
+    st, r = make(M, V, H, seed=21, scale=2.0, groups=[(Dz, V)])
+    z = torch.rand(B, Dz, generator=torch.Generator().manual_seed(2))
+    y = O.synthetic_labels(B, K, seed=3)
+    mu = torch.rand(B, Dz, generator=torch.Generator().manual_seed(4))
+    vk = torch.zeros(B, V); km = torch.zeros(B, V); vk[:, Dz:] = y; km[:, Dz:] = 1
+    ref = O.noisy_meanfield(st, vk, km, n_steps=20, mu_pull=(mu, 0.15), fld=RandomField(31, 0))
+    r._mu_pull = {"mu_k": mu.to(DEV), "eta0": 0.15}
+    r.set_rng(31, 0)
+    out = r.noisy_meanfield_annealed(vk.to(DEV), km.to(DEV), n_steps=20)
+    r._mu_pull = None
+    torch.testing.assert_close(out.cpu(), ref, rtol=0, atol=3e-3)
+    vk = torch.zeros(B, V); km = torch.zeros(B, V); vk[:, :Dz] = z; km[:, :Dz] = 1
+    ref = O.conditional_gibbs(st, vk, km, n_steps=20, fld=RandomField(31, 1))
+    r.set_rng(31, 1)
+    out = r.conditional_gibbs(vk.to(DEV), km.to(DEV), n_steps=20)
+    torch.testing.assert_close(out.cpu(), ref, rtol=0, atol=3e-3)
+    assert torch.allclose(out[:, Dz:].sum(1).cpu(), torch.ones(B), atol=1e-4)

@@ -5,6 +5,7 @@ import torch
 import multimodal_idbn_b200 as M
 dev = "cuda"
 V, H, Dz, K = 532, 256, 500, 32
+M.set_precision(os.environ.get("PREC", "tf32"))
 r = M.RBM(V, H, 0.04, 1e-4, 0.5, softmax_groups=[(Dz, V)]).to(dev)
 with torch.no_grad():
     r.W.data.mul_(3.0)
