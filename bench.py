@@ -239,6 +239,10 @@ def run_ours(args):
     sb = step_bytes(LAYERS, CD_K)
     step_gbs = sb / (ms / steps * 1e-3) / 1e9
 
+    # ---------------- second metric of BASELINE.json: cross-modal chain-steps/s (config C4 shapes,
+    # this rank's share of the 65 536 chains: joint RBM (500+32)->256, 50 steps, both directions)
+    chains = chain_steps_metric(M, dev, 65536 // max(1, world) if world > 1 else 8192)
+
     if rank != 0:
         return
     cpu = cpu_baseline() if world == 1 and not args.no_cpu_baseline else None
@@ -265,8 +269,36 @@ def run_ours(args):
                             (v["ms_avg"] * 1e-3) / 1e9 if v["ms_avg"] else None) for k, v in kern.items()},
         "roofline_step": {"algorithmic_bytes": sb, "achieved_gbs": step_gbs, "frac": step_gbs / peak},
         "cpu_baseline": cpu,
+        "extra": {"chain_steps_per_s": chains},
     }
     print(json.dumps(line), flush=True)
+
+
+def chain_steps_metric(M, dev, n_chains, steps=50):
+    """IMG->TXT conditional Gibbs and TXT->IMG noisy mean-field annealing (iMDBN._cross_reconstruct,
+    imdbn.py:419-449) on `n_chains` chains; device-timed, chain-steps/s per direction (this rank)."""
+    Dz, K, H = 500, 32, 256
+    V = Dz + K
+    torch.manual_seed(3)
+    r = M.RBM(V, H, 0.04, 1e-4, 0.5, softmax_groups=[(Dz, V)]).to(dev)
+    z = torch.rand(n_chains, Dz, device=dev)
+    y = torch.nn.functional.one_hot(torch.randint(0, K, (n_chains,), device=dev), K).float()
+    vk1 = torch.zeros(n_chains, V, device=dev); km1 = torch.zeros_like(vk1); vk1[:, :Dz] = z; km1[:, :Dz] = 1
+    vk2 = torch.zeros(n_chains, V, device=dev); km2 = torch.zeros_like(vk2); vk2[:, Dz:] = y; km2[:, Dz:] = 1
+    mu = torch.rand(n_chains, Dz, device=dev)
+    out = {"chains": n_chains, "steps": steps}
+    for name, fn in (("img2txt_cond_gibbs", lambda: r.conditional_gibbs(vk1, km1, n_steps=steps)),
+                     ("txt2img_noisy_mf", lambda: r.noisy_meanfield_annealed(vk2, km2, n_steps=steps))):
+        r._mu_pull = {"mu_k": mu, "eta0": 0.15} if name.startswith("txt2img") else None
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        out[name] = n_chains * steps * 3 / (e0.elapsed_time(e1) * 1e-3)
+    r._mu_pull = None
+    return out
 
 
 def main():
@@ -275,7 +307,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"])
+    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
