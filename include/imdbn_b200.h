@@ -122,6 +122,18 @@ int imdbn_cd_train(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* data, int 
                    const imdbn_update* upd, const imdbn_rng* rng, float* loss_out,
                    imdbn_stream stream);
 
+/* RBM.train_epoch followed by the `v = rbm.forward(v)` of the iDBN training loop (idbn.py:202-203), with
+ * one optimisation of the traffic: the forward pass with the UPDATED weights also computes, in the same
+ * pass over W, the positive hidden probabilities of the NEXT minibatch (which uses those same weights).
+ *   pos_h_in  nullable [B,H]      : positive probabilities of `data` produced by the previous call
+ *   next_data nullable [B_next,V] : the next minibatch
+ *   fwd_out   [B + B_next, H]     : rows [0,B) = forward(data), rows [B,..) = forward(next_data),
+ *                                   both with the updated parameters */
+int imdbn_cd_train_fwd(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* data, int B, int k,
+                       const imdbn_update* upd, const imdbn_rng* rng, float* loss_out,
+                       const float* pos_h_in, const float* next_data, int B_next, float* fwd_out,
+                       imdbn_stream stream);
+
 /* The same statistics without the update, for batches sharded over ranks: writes the local sums
  *   stats_out = [ dS (V*H) | dh (H) | dv (V) | pos_h column sum (H) | squared error (1) ]
  * which the host all-reduces (NCCL) and hands to imdbn_apply_update on every rank. */

@@ -77,6 +77,8 @@ SIGNATURES = {
     "imdbn_free_energy": (_I, [_P, C.POINTER(RbmStruct), _P, _I, _P, _P]),
     "imdbn_cd_train": (_I, [_P, C.POINTER(RbmStruct), _P, _I, _I, C.POINTER(UpdateStruct),
                             C.POINTER(RngStruct), _P, _P]),
+    "imdbn_cd_train_fwd": (_I, [_P, C.POINTER(RbmStruct), _P, _I, _I, C.POINTER(UpdateStruct),
+                                C.POINTER(RngStruct), _P, _P, _P, _I, _P, _P]),
     "imdbn_cd_stats": (_I, [_P, C.POINTER(RbmStruct), _P, _I, _I, C.POINTER(RngStruct), _P, _P]),
     "imdbn_stats_size": (C.c_int64, [C.POINTER(RbmStruct)]),
     "imdbn_apply_update": (_I, [_P, C.POINTER(RbmStruct), _P, C.POINTER(UpdateStruct), _P, _P]),

@@ -38,6 +38,7 @@ struct imdbn_ctx {
     // transposed-weight cache for the chain kernels is rebuilt on every call (W changes between
     // updates); it lives in the arena like everything else.
     void* tc = nullptr;  // tensor-core path state (tc_gemm.cu), opaque here
+    bool stats_after_colstats = false;   // next tc statistics kernel directly follows k_colstats (see tc_stats.cuh)
     unsigned int* ticket = nullptr;   // device counter of the last-block reductions (self-resetting)
 };
 

@@ -362,9 +362,18 @@ int run_chain(imdbn_ctx* ctx, const imdbn_rbm* r, const imdbn_chain* ch, int B, 
 }
 
 // shared body of cd_train / cd_stats
+// Optional tail of a CD update (imdbn_cd_train_fwd): forward(data) with the UPDATED weights
+// (idbn.py:203) and, in the same pass over W, the positive phase of the next minibatch.
+struct FwdTail {
+    const float* pos_h_in;     // nullable: positive probabilities of `data` from the previous call
+    const float* next_data;    // nullable [B_next, V]
+    int B_next;
+    float* fwd_out;            // nullable [B + B_next, H]
+};
+
 int cd_core(imdbn_ctx* ctx, const imdbn_rbm* r, const float* data, int B, int k,
             const imdbn_update* upd, const imdbn_rng* rng, float* loss_out, float* stats_out,
-            cudaStream_t st) {
+            cudaStream_t st, const FwdTail* tail = nullptr) {
     int rc = check_rbm(ctx, r, stats_out == nullptr);
     if (rc) return rc;
     IMDBN_ARG(ctx, data && B > 0 && k >= 1 && rng);
@@ -372,9 +381,15 @@ int cd_core(imdbn_ctx* ctx, const imdbn_rbm* r, const float* data, int B, int k,
     const PassPlan pu = plan_pass(ctx, r, B, true), pd = plan_pass(ctx, r, B, false);
     const size_t nBH = (size_t)B * H, nBV = (size_t)B * V;
     const int nb_sq = colstat_blocks(r);
+    const bool do_fwd = tail && tail->fwd_out;
+    if (tail && tail->next_data)
+        IMDBN_ARG(ctx, V % 4 == 0 && al16(data) && al16(tail->next_data));
+    const int Bt = do_fwd ? B + (tail->next_data ? tail->B_next : 0) : 0;
+    PassPlan pf{};
+    if (do_fwd) pf = plan_pass(ctx, r, Bt, true);
     size_t bytes = pad256(std::max(pu.part_floats, pd.part_floats)) + 3 * pad256(nBH) +
                    4 * pad256(nBV) + pad256(2 * H + V + 1) + pad256(nb_sq) +
-                   tc_ws_bytes(ctx, r, B);
+                   tc_ws_bytes(ctx, r, B) + (do_fwd ? pad256(pf.part_floats) + pad256((size_t)Bt * V) : 0);
     rc = arena_begin(ctx, bytes, st);
     if (rc) return rc;
     float* part = arena_take<float>(ctx, std::max(pu.part_floats, pd.part_floats));
@@ -388,8 +403,15 @@ int cd_core(imdbn_ctx* ctx, const imdbn_rbm* r, const float* data, int B, int k,
     float* sq_part = arena_take<float>(ctx, nb_sq);
     const RngKey key = make_key(rng);
 
-    rc = up_pass(ctx, r, data, B, 1.0f, pos_h, h_s, key, 0, pu, part, st);          // rbm.py:199,203
-    if (rc) return rc;
+    if (tail && tail->pos_h_in) {
+        // positive phase already computed together with the previous call's forward pass
+        pos_h = const_cast<float*>(tail->pos_h_in);
+        k_bernoulli<<<ew_blocks(nBH, ctx->num_sms), 256, 0, st>>>(pos_h, B, H, h_s, key, 0);      // rbm.py:203
+        IMDBN_CHECK_LAUNCH(ctx, "k_bernoulli");
+    } else {
+        rc = up_pass(ctx, r, data, B, 1.0f, pos_h, h_s, key, 0, pu, part, st);      // rbm.py:199,203
+        if (rc) return rc;
+    }
     for (int s = 0; s < k; ++s) {
         rc = down_pass(ctx, r, h_s, B, 1.0f, v_prob, nullptr, v_s, lg_tmp, key, 1 + 3 * s,
                        2 + 3 * s, pd, part, st);                                        // :205-206
@@ -398,12 +420,29 @@ int cd_core(imdbn_ctx* ctx, const imdbn_rbm* r, const float* data, int B, int k,
                      part, st);                                                         // :207-208
         if (rc) return rc;
     }
-    // bias / loss statistics must read W-independent buffers only, so order vs. the fused weight
-    // update does not matter; keep the reference's order (weights first).
-    rc = gemm_stats(ctx, r, data, pos_h, v_s, h_prob, B, stats_out, upd, st);           // :200,209,212
+    // The bias / loss kernel and the weight-statistics kernel share only read-only inputs (the biases are
+    // not read by the statistics GEMM, W is not read by the column statistics), so their order does not
+    // matter; the column statistics go first and the tensor-core statistics kernel overlaps them.
+    rc = finish_stats(ctx, r, pos_h, h_prob, data, v_s, data, v_prob, B, st_small, sq_part, upd, loss_out,
+                      stats_out == nullptr, st);                                        // :216-226
     if (rc) return rc;
-    return finish_stats(ctx, r, pos_h, h_prob, data, v_s, data, v_prob, B, st_small, sq_part, upd, loss_out,
-                        stats_out == nullptr, st);
+    ctx->stats_after_colstats = true;
+    rc = gemm_stats(ctx, r, data, pos_h, v_s, h_prob, B, stats_out, upd, st);           // :200,209,212
+    ctx->stats_after_colstats = false;
+    if (rc || !do_fwd) return rc;
+    // one pass over the updated W for [data ; next_data]
+    const float* src = data;
+    if (Bt > B) {
+        float* cat = arena_take<float>(ctx, (size_t)Bt * V);
+        const size_t n1 = nBV / 4, n2 = (size_t)tail->B_next * V / 4;      // V % 4 == 0 on this path
+        k_concat2<<<ew_blocks(n1 + n2, ctx->num_sms), 256, 0, st>>>(
+            reinterpret_cast<const float4*>(data), n1, reinterpret_cast<const float4*>(tail->next_data), n2,
+            reinterpret_cast<float4*>(cat));
+        IMDBN_CHECK_LAUNCH(ctx, "k_concat2");
+        src = cat;
+    }
+    float* part_f = arena_take<float>(ctx, pf.part_floats);
+    return up_pass(ctx, r, src, Bt, 1.0f, tail->fwd_out, nullptr, key, 0, pf, part_f, st);
 }
 
 int clamped_core(imdbn_ctx* ctx, const imdbn_rbm* r, const float* v_known, const float* km, int B,
@@ -507,12 +546,15 @@ int clamped_core(imdbn_ctx* ctx, const imdbn_rbm* r, const float* v_known, const
         IMDBN_CUDA(ctx, cudaMemcpyAsync(v_neg, v_plus, nBV * sizeof(float), cudaMemcpyDeviceToDevice, st));
     rc = up_pass(ctx, r, v_neg, B, 1.0f, h_neg, nullptr, key, 0, pu, part, st);         // :471
     if (rc) return rc;
-    rc = gemm_stats(ctx, r, v_plus, h_plus, v_neg, h_neg, B, stats_out, upd, st);       // :456,472,476
-    if (rc) return rc;
     imdbn_update u{};
     if (upd) { u = *upd; u.sparsity = 0; }                                              // :478-481
-    return finish_stats(ctx, r, h_plus, h_neg, v_plus, v_neg, v_plus, v_neg, B, st_small, sq_part, &u,
-                        loss_out, stats_out == nullptr, st);
+    rc = finish_stats(ctx, r, h_plus, h_neg, v_plus, v_neg, v_plus, v_neg, B, st_small, sq_part, &u,
+                      loss_out, stats_out == nullptr, st);
+    if (rc) return rc;
+    ctx->stats_after_colstats = true;
+    rc = gemm_stats(ctx, r, v_plus, h_plus, v_neg, h_neg, B, stats_out, upd, st);       // :456,472,476
+    ctx->stats_after_colstats = false;
+    return rc;
 }
 
 }  // namespace
@@ -670,6 +712,14 @@ int imdbn_cd_train(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* data, int 
                    imdbn_stream stream) {
     IMDBN_ARG(ctx, upd && upd->batch_global > 0);
     return cd_core(ctx, rbm, data, B, k, upd, rng, loss_out, nullptr, (cudaStream_t)stream);
+}
+
+int imdbn_cd_train_fwd(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* data, int B, int k,
+                       const imdbn_update* upd, const imdbn_rng* rng, float* loss_out, const float* pos_h_in,
+                       const float* next_data, int B_next, float* fwd_out, imdbn_stream stream) {
+    IMDBN_ARG(ctx, upd && upd->batch_global > 0 && fwd_out && (!next_data || B_next > 0));
+    FwdTail t{pos_h_in, next_data, next_data ? B_next : 0, fwd_out};
+    return cd_core(ctx, rbm, data, B, k, upd, rng, loss_out, nullptr, (cudaStream_t)stream, &t);
 }
 
 int64_t imdbn_stats_size(const imdbn_rbm* r) {

@@ -138,8 +138,11 @@ k_colstats(const float* __restrict__ hp, const float* __restrict__ hn, const flo
            BiasArgs ba) {
     __shared__ float red[5][CS_ROWS][CS_COLS];
     __shared__ unsigned int s_last;
-    pdl_trigger();
+    // Trigger AFTER the wait: the kernel launched next (the statistics GEMM, which only shares read-only
+    // inputs with this one) may then start immediately and run CONCURRENTLY with this kernel -- everything
+    // before this kernel has completed by the time the trigger fires.
     pdl_wait();
+    pdl_trigger();
     const int x = threadIdx.x % CS_COLS, y = threadIdx.x / CS_COLS;
     const int c = blockIdx.x * CS_COLS + x;
     float ha = 0.f, hb_ = 0.f, va = 0.f, vb_ = 0.f, sq = 0.f;
@@ -338,6 +341,14 @@ __global__ void k_class_stats(const float* __restrict__ z, const float* __restri
         class_count[d] += cnt;
         label_sum[d] += ls;
     }
+}
+
+// out = [a ; b] (float4 granularity)
+__global__ void k_concat2(const float4* __restrict__ a, size_t na, const float4* __restrict__ b, size_t nb,
+                          float4* __restrict__ out) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < na + nb;
+         i += (size_t)gridDim.x * blockDim.x)
+        out[i] = i < na ? a[i] : b[i - na];
 }
 
 __global__ void k_random_field(RngKey key, uint32_t draw, int kind, int rows, int cols,

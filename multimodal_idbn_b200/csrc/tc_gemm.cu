@@ -310,7 +310,11 @@ template <bool A_MN>
 static int launch_stream(imdbn_ctx* ctx, const CUtensorMap* tmA, const CUtensorMap* tmB, StreamArgs& a, int G,
                          int chunks, cudaStream_t st) {
     const size_t smem = (size_t)a.stages * ts_stage_bytes(a.Npad) + 1024 + 256;
-    IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_tc_stream<A_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static size_t smem_set = 0;          // the attribute is sticky: raise it only when a larger size is needed
+    if (smem > smem_set) {
+        IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_tc_stream<A_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
     IMDBN_CUDA(ctx, launch_pdl(k_tc_stream<A_MN>, dim3(G, chunks), dim3(TS_THREADS), smem, st, *tmA, *tmB, a));
     IMDBN_CHECK_LAUNCH(ctx, "k_tc_stream");
     return 0;
@@ -357,6 +361,8 @@ int tc_gemm_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* vp, const flo
     a.k_chunks = (B + ST_KC - 1) / ST_KC;
     if (upd) { a.lr = upd->lr; a.mom = upd->momentum; a.wd = upd->weight_decay; a.bsz = (float)upd->batch_global; }
     a.dbg = 0;
+    a.late_wait = ctx->stats_after_colstats ? 1 : 0;
+    ctx->stats_after_colstats = false;
     a.w_policy = l2_policy_env("IMDBN_L2_W", L2_EVICT_NORMAL);
     a.wm_policy = l2_policy_env("IMDBN_L2_WM", L2_EVICT_NORMAL);
     const CUtensorMap* tVP = get_map(ctx, vp, r->V, B, ST_KC, true);
@@ -368,10 +374,12 @@ int tc_gemm_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* vp, const flo
     if (!tVP || !tVN || !tHP || !tHN || !tW || !tWm) return fail(ctx, -5, "cuTensorMapEncodeTiled failed");
     const int G = std::min(ctx->num_sms, a.m_tiles * a.n_tiles);
     if (dS_out) {
-        IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_tc_stats<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
+        static bool set0 = false;
+        if (!set0) { IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_tc_stats<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM)); set0 = true; }
         IMDBN_CUDA(ctx, launch_pdl(k_tc_stats<false>, dim3(G), dim3(ST_THREADS), ST_SMEM, st, *tVP, *tVN, *tHP, *tHN, *tW, *tWm, a));
     } else {
-        IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_tc_stats<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
+        static bool set1 = false;
+        if (!set1) { IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_tc_stats<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM)); set1 = true; }
         IMDBN_CUDA(ctx, launch_pdl(k_tc_stats<true>, dim3(G), dim3(ST_THREADS), ST_SMEM, st, *tVP, *tVN, *tHP, *tHN, *tW, *tWm, a));
     }
     IMDBN_CHECK_LAUNCH(ctx, "k_tc_stats");

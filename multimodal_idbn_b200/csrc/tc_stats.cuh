@@ -37,6 +37,7 @@ struct StatsArgs {
     int m_tiles, n_tiles, k_chunks;
     float lr, mom, wd, bsz;
     uint64_t w_policy, wm_policy;   // L2 eviction priorities of the W and W_m streams
+    int late_wait;
     int dbg;    // experiment switch (IMDBN_DEBUG_STATS): 1 = no operands/MMA, 2 = no W/W_m traffic
 };
 
@@ -84,7 +85,10 @@ k_tc_stats(const __grid_constant__ CUtensorMap tmVP, const __grid_constant__ CUt
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    pdl_wait();                 // everything above overlapped the previous kernel's tail
+    // late_wait: the predecessor is k_colstats, which fires its trigger only after ITS predecessors have
+    // completed and touches nothing this kernel reads or writes: run concurrently with it and restore
+    // the completion chain with a wait at the very end.
+    if (!a.late_wait) pdl_wait();
 
     if (warp == 0) {
         // ===================== operand producer =====================
@@ -248,6 +252,7 @@ k_tc_stats(const __grid_constant__ CUtensorMap tmVP, const __grid_constant__ CUt
         }
     }
 
+    if (a.late_wait) pdl_wait();
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {

@@ -148,14 +148,18 @@ class iDBN:
 
     # ------------------------------------------------------------------ training
     @torch.no_grad()
-    def train_step(self, v: torch.Tensor, epoch: int, epochs: int) -> List[torch.Tensor]:
+    def train_step(self, v: torch.Tensor, epoch: int, epochs: int,
+                   next_v: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
         """One minibatch of the hot loop (idbn.py:200-204); returns the per-layer losses as device
-        scalars (no host synchronisation)."""
+        scalars (no host synchronisation).  ``next_v`` = the next minibatch if already known (flattened
+        fp32 on the device, the SAME tensor object that will be passed as ``v`` next time): the first
+        layer then computes its positive phase in this step's post-update forward pass."""
         v = _flat(v, self.device)
         losses = []
-        for rbm in self.layers:
-            losses.append(rbm.train_epoch(v, epoch, epochs, CD=self.cd_k))
-            v = rbm.forward(v)
+        for i, rbm in enumerate(self.layers):
+            loss, v = rbm.train_epoch_fwd(v, epoch, epochs, CD=self.cd_k,
+                                          next_data=next_v if i == 0 else None)
+            losses.append(loss)
         return losses
 
     def train(self, epochs: int, log_every_pca: int = 25, log_every_probe: int = 10):
@@ -163,8 +167,14 @@ class iDBN:
         loss of every epoch (one device->host read per epoch)."""
         for epoch in range(int(epochs)):
             losses: List[torch.Tensor] = []
+            cur = None
             for batch in prefetch_to_device(self.dataloader, self.device):
-                losses.extend(self.train_step(batch[0], epoch, epochs))
+                nxt = _flat(batch[0], self.device)
+                if cur is not None:
+                    losses.extend(self.train_step(cur, epoch, epochs, next_v=nxt))
+                cur = nxt
+            if cur is not None:
+                losses.extend(self.train_step(cur, epoch, epochs))
             if losses:
                 mean_loss = float(torch.stack(losses).mean())
                 self.loss_history.append(mean_loss)

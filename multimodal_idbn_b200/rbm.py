@@ -215,6 +215,7 @@ class RBM(nn.Module):
         lr, mom = self._hyper(epoch)
         rs = self._struct(training=True)
         loss = torch.empty((), device=data.device, dtype=torch.float32)
+        self._n_updates = getattr(self, "_n_updates", 0) + 1
         dp = _dist.state()
         if dp is None:
             rng = self._next_rng()
@@ -232,6 +233,48 @@ class RBM(nn.Module):
         ctx.check(ctx.lib.imdbn_apply_update(ctx.handle, C.byref(rs), L.ptr(stats), C.byref(upd),
                                              L.ptr(loss), st), "imdbn_apply_update")
         return loss
+
+    @torch.no_grad()
+    def train_epoch_fwd(self, data: torch.Tensor, epoch: int, max_epochs: int, CD: int = 1,
+                        next_data: Optional[torch.Tensor] = None):
+        """``loss = train_epoch(data, ...); h = forward(data)`` as the iDBN training loop issues them
+        (reference idbn.py:202-203), returned as ``(loss, h)``.  When ``next_data`` (the next minibatch of
+        the same loader) is given, the forward pass also computes its positive hidden probabilities in the
+        same pass over the updated ``W`` and keeps them for the next call, which then skips its first up
+        pass: one 4*V*H-byte stream of ``W`` less per minibatch, bit-identical results."""
+        data = self._in(data, self.num_visible)
+        if _dist.state() is not None:
+            return self.train_epoch(data, epoch, max_epochs, CD), self.forward(data)
+        ctx, st = self._ctx()
+        B = data.shape[0]
+        lr, mom = self._hyper(epoch)
+        rs = self._struct(training=True)
+        loss = torch.empty((), device=data.device, dtype=torch.float32)
+        rng = self._next_rng()
+        upd = self._update_struct(lr, mom, B, self.sparsity)
+        cached = self.__dict__.pop("_pos_cache", None)
+        pos_in = None
+        if cached is not None:
+            key, pos = cached
+            if key == self._pos_key(data):
+                pos_in = pos
+        nxt, Bn = None, 0
+        if next_data is not None:
+            nxt = self._in(next_data, self.num_visible)
+            Bn = nxt.shape[0]
+        fwd = torch.empty(B + Bn, self.num_hidden, device=data.device, dtype=torch.float32)
+        ctx.check(ctx.lib.imdbn_cd_train_fwd(ctx.handle, C.byref(rs), L.ptr(data), B, int(CD), C.byref(upd),
+                                             C.byref(rng), L.ptr(loss), L.ptr(pos_in), L.ptr(nxt), Bn,
+                                             L.ptr(fwd), st), "imdbn_cd_train_fwd")
+        self._n_updates = getattr(self, "_n_updates", 0) + 1
+        if nxt is not None:
+            self._pos_cache = (self._pos_key(nxt), fwd[B:])
+        return loss, fwd[:B]
+
+    def _pos_key(self, x: torch.Tensor):
+        """Identity of (input buffer, parameter state) under which cached positive probabilities hold."""
+        return (x.data_ptr(), tuple(x.shape), x._version, self.W.data_ptr(), self.W._version,
+                self.hid_bias._version, getattr(self, "_n_updates", 0))
 
     def _stats_buffer(self, ctx, rs) -> torch.Tensor:
         n = int(ctx.lib.imdbn_stats_size(C.byref(rs)))
@@ -361,6 +404,7 @@ class RBM(nn.Module):
         cfg = L.ClampedCfgStruct(int(CD), int(cond_init_steps), int(sample_h), int(sample_v),
                                  int(reclamp_negative), int(use_noisy_init))
         loss = torch.empty((), device=vk.device, dtype=torch.float32)
+        self._n_updates = getattr(self, "_n_updates", 0) + 1
         dp = _dist.state()
         if dp is None:
             rng = self._next_rng()
@@ -384,6 +428,7 @@ class RBM(nn.Module):
     def __getstate__(self):
         state = dict(self.__dict__)
         state.pop("_stats_buf", None)       # scratch, not model state
+        state.pop("_pos_cache", None)
         return state
 
 
