@@ -65,12 +65,73 @@ __device__ __forceinline__ void chain_dot(const float* __restrict__ wcol, int ld
     }
 }
 
-template <int R>
-__global__ void __launch_bounds__(CHAIN_THREADS) k_chain(ChainArgs a) {
+// raw[r][n] = sum_k xs[r][k] * w[k*ld + n] for n < N, K-SLICED: the thread block is arranged as
+// (N/4 column quads) x (S k-slices); every thread streams float4 weights for its quad over its slice of
+// k with 16 loads in flight, the S partial sums are added in slice order.  Used when few chains share a
+// CTA (small batches), where one thread per column would serialise ~K/16 L2 round trips.
+template <int R, int NT>
+__device__ __forceinline__ void chain_matvec_sliced(const float* __restrict__ w, int ld, int K, int Kp, int N,
+                                                    int Np, const float* __restrict__ xs, float* __restrict__ part,
+                                                    float* __restrict__ raw) {
+    const int tid = threadIdx.x;
+    const int ncg = Np >> 2;
+    int S = NT / ncg; S = S > 8 ? 8 : (S < 1 ? 1 : S);
+    const int kper = (((Kp + S - 1) / S) + 3) & ~3;
+    for (int base = 0; base < ncg; base += NT) {            // (ncg > NT only for very wide layers)
+        const int t = tid;
+        const int cg = base + (S > 1 ? t % ncg : t), sl = S > 1 ? t / ncg : 0;
+        if (cg < ncg && sl < S) {
+            float acc[R][4];
+#pragma unroll
+            for (int r = 0; r < R; ++r) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f; }
+            const int k0 = sl * kper, k1 = min(Kp, k0 + kper);
+            const float* wp = w + 4 * cg;
+            const bool col_ok = 4 * cg < N;
+            for (int k = k0; k < k1; k += 16) {
+                float4 wv[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q)
+                    wv[q] = (col_ok && k + q < k1 && k + q < K)
+                                ? __ldg(reinterpret_cast<const float4*>(wp + (size_t)(k + q) * ld))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    if (k + q < k1) {
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const float x = xs[r * Kp + k + q];
+                            acc[r][0] = fmaf(x, wv[q].x, acc[r][0]);
+                            acc[r][1] = fmaf(x, wv[q].y, acc[r][1]);
+                            acc[r][2] = fmaf(x, wv[q].z, acc[r][2]);
+                            acc[r][3] = fmaf(x, wv[q].w, acc[r][3]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                *reinterpret_cast<float4*>(part + ((size_t)sl * R + r) * Np + 4 * cg) =
+                    make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < R * Np; i += NT) {
+        float v = 0.f;
+        for (int sl = 0; sl < S; ++sl) v += part[(size_t)sl * R * Np + i];
+        raw[i] = v;
+    }
+    __syncthreads();
+}
+
+template <int R, int NT, bool SLICED>
+__global__ void __launch_bounds__(NT) k_chain(ChainArgs a) {
+    constexpr int CHAIN_THREADS = NT;     // shadows the namespace constant inside this kernel
     extern __shared__ __align__(16) float smem[];
     float* vs = smem;                     // [R][Vp] current visible state
     float* hs = vs + R * a.Vp;            // [R][Hp] hidden state
     float* lg = hs + R * a.Hp;            // [R][Vp] visible logits / probabilities
+    float* raw = lg + R * a.Vp;           // SLICED only: [R][max(Vp,Hp)] products, then [8][R][max] partials
+    float* part = raw + R * max(a.Vp, a.Hp);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int row_base = blockIdx.x * R;
@@ -107,12 +168,13 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain(ChainArgs a) {
         else       { d_h = a.draw0 + 1 + 3 * t; d_v = a.draw0 + 2 + 3 * t; d_c = a.draw0 + 3 + 3 * t; }
 
         // ---- h | v : h = sigmoid((vW + hb)/T + sig*N)                          rbm.py:344-347,394
+        if (SLICED) chain_matvec_sliced<R, NT>(a.W, a.H, a.V, a.Vp, a.H, a.Hp, vs, part, raw);
         for (int j = tid; j < a.Hp; j += CHAIN_THREADS) {
             if (j >= a.H) continue;
             float acc[R];
 #pragma unroll
-            for (int r = 0; r < R; ++r) acc[r] = 0.0f;
-            chain_dot<R>(a.W + j, a.H, a.V, a.Vp, vs, acc);
+            for (int r = 0; r < R; ++r) acc[r] = SLICED ? raw[r * a.Hp + j] : 0.0f;
+            if (!SLICED) chain_dot<R>(a.W + j, a.H, a.V, a.Vp, vs, acc);
             const float bj = a.hb[j];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
@@ -127,12 +189,13 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain(ChainArgs a) {
         __syncthreads();
 
         // ---- v | h : logits = (h W^T + vb)/T + sig*N                           rbm.py:350-352,396
+        if (SLICED) chain_matvec_sliced<R, NT>(a.Wt, a.V, a.H, a.Hp, a.V, a.Vp, hs, part, raw);
         for (int c = tid; c < a.Vp; c += CHAIN_THREADS) {
             if (c >= a.V) continue;
             float acc[R];
 #pragma unroll
-            for (int r = 0; r < R; ++r) acc[r] = 0.0f;
-            chain_dot<R>(a.Wt + c, a.V, a.H, a.Hp, hs, acc);
+            for (int r = 0; r < R; ++r) acc[r] = SLICED ? raw[r * a.Vp + c] : 0.0f;
+            if (!SLICED) chain_dot<R>(a.Wt + c, a.V, a.H, a.Hp, hs, acc);
             const float bc = a.vb[c];
 #pragma unroll
             for (int r = 0; r < R; ++r) {

@@ -225,12 +225,12 @@ int bias_update(imdbn_ctx* ctx, const imdbn_rbm* r, float* st_small, const imdbn
 }
 
 // ---- chain launcher -------------------------------------------------------------------------
-template <int R>
+template <int R, int NT, bool SLICED>
 int launch_chain_r(imdbn_ctx* ctx, const ChainArgs& a, size_t smem, cudaStream_t st) {
     ProfScope prof(ctx, IMDBN_KERNEL_CHAIN, a.V, a.H, st);
-    IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_chain<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_chain<R, NT, SLICED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem));
-    k_chain<R><<<(a.B + R - 1) / R, CHAIN_THREADS, smem, st>>>(a);
+    k_chain<R, NT, SLICED><<<(a.B + R - 1) / R, NT, smem, st>>>(a);
     IMDBN_CHECK_LAUNCH(ctx, "k_chain");
     return 0;
 }
@@ -350,14 +350,19 @@ int run_chain(imdbn_ctx* ctx, const imdbn_rbm* r, const imdbn_chain* ch, int B, 
     const size_t per_row = (size_t)(2 * a.Vp + a.Hp) * sizeof(float);
     int R = 16;
     while (R > 1 && ((B + R - 1) / R < 2 * ctx->num_sms || per_row * R > 100 * 1024)) R >>= 1;
-    const size_t smem = per_row * R;
+    size_t smem = per_row * R;
+    // few chains per CTA: k-sliced float4 products with 512 threads (see chain_matvec_sliced)
+    const bool sliced = R <= 2 && (r->V % 4) == 0 && (r->H % 4) == 0 && al16(r->W) && al16(Wt);
+    if (sliced) smem += (size_t)9 * R * std::max(a.Vp, a.Hp) * sizeof(float);
     if (smem > 227 * 1024) return fail(ctx, -2, "chain state does not fit in shared memory");
+    if (sliced) return R == 2 ? launch_chain_r<2, 512, true>(ctx, a, smem, st)
+                              : launch_chain_r<1, 512, true>(ctx, a, smem, st);
     switch (R) {
-        case 16: return launch_chain_r<16>(ctx, a, smem, st);
-        case 8:  return launch_chain_r<8>(ctx, a, smem, st);
-        case 4:  return launch_chain_r<4>(ctx, a, smem, st);
-        case 2:  return launch_chain_r<2>(ctx, a, smem, st);
-        default: return launch_chain_r<1>(ctx, a, smem, st);
+        case 16: return launch_chain_r<16, 256, false>(ctx, a, smem, st);
+        case 8:  return launch_chain_r<8, 256, false>(ctx, a, smem, st);
+        case 4:  return launch_chain_r<4, 256, false>(ctx, a, smem, st);
+        case 2:  return launch_chain_r<2, 256, false>(ctx, a, smem, st);
+        default: return launch_chain_r<1, 256, false>(ctx, a, smem, st);
     }
 }
 
