@@ -210,17 +210,31 @@ def run_ours(args):
 
     def e2e_loop(n, off):
         loader = [(host[(off + i) % N_DISTINCT_BATCHES],) for i in range(n)]
-        cur, i = None, 0
+        cur, i, pending = None, 0, None
+        main = torch.cuda.current_stream(dev)
+
+        def read_back(p):                                      # D2H read of a finished step's result
+            row, losses, ev = p
+            if ev is not None:
+                main.wait_event(ev)                            # upper layers run on a side stream
+            loss_host[row].copy_(torch.stack(losses), non_blocking=True)
+
         for b in M.prefetch_to_device(loader, dev):            # same lookahead loop as iDBN.train
             nxt = b[0]
             if cur is not None:
                 losses = model.train_step(cur, 0, 1, next_v=nxt)
-                loss_host[off + i].copy_(torch.stack(losses), non_blocking=True)   # D2H read of the result
+                if pending is not None:
+                    read_back(pending)                         # step t-1 is read while step t is enqueued
+                pending = (off + i, losses, getattr(model, "loss_ready", None))
                 i += 1
             cur = nxt
         if cur is not None:
             losses = model.train_step(cur, 0, 1)
-            loss_host[off + i].copy_(torch.stack(losses), non_blocking=True)
+            if pending is not None:
+                read_back(pending)
+            pending = (off + i, losses, getattr(model, "loss_ready", None))
+        if pending is not None:
+            read_back(pending)
 
     e2e_loop(warm, 0)
     barrier()

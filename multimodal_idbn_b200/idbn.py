@@ -155,12 +155,45 @@ class iDBN:
         fp32 on the device, the SAME tensor object that will be passed as ``v`` next time): the first
         layer then computes its positive phase in this step's post-update forward pass."""
         v = _flat(v, self.device)
-        losses = []
-        for i, rbm in enumerate(self.layers):
-            loss, v = rbm.train_epoch_fwd(v, epoch, epochs, CD=self.cd_k,
-                                          next_data=next_v if i == 0 else None)
-            losses.append(loss)
+        if len(self.layers) == 1 or not getattr(self, "pipeline_layers", False) or v.device.type != "cuda":
+            losses = []
+            for i, rbm in enumerate(self.layers):
+                loss, v = rbm.train_epoch_fwd(v, epoch, epochs, CD=self.cd_k,
+                                              next_data=next_v if i == 0 else None)
+                losses.append(loss)
+            return losses
+        # Optional (pipeline_layers = True; measured slower on B200 because the 197 KB tensor-core CTAs of the
+        # two layers cannot share an SM, so it is off by default):
+        # Layer 0 of minibatch t+1 does not depend on the upper layers of minibatch t (they only consume
+        # layer 0's forward output), so the upper layers run on a side stream and overlap the next
+        # layer-0 update.  Results are identical; `sync()` (or `loss_ready`) orders readers of the losses.
+        main = torch.cuda.current_stream(v.device)
+        side = self.__dict__.get("_side_stream")
+        if side is None:
+            side = self._side_stream = torch.cuda.Stream(device=v.device)
+        loss0, h = self.layers[0].train_epoch_fwd(v, epoch, epochs, CD=self.cd_k, next_data=next_v)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        h.record_stream(side)
+        losses = [loss0]
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
+            x = h
+            for rbm in self.layers[1:]:
+                loss, x = rbm.train_epoch_fwd(x, epoch, epochs, CD=self.cd_k)
+                loss.record_stream(main)
+                losses.append(loss)
+            done = torch.cuda.Event()
+            done.record(side)
+        self.loss_ready = done
         return losses
+
+    def sync(self) -> None:
+        """Make the current stream wait for the upper layers' side stream (call before reading losses or
+        the upper layers' parameters on the current stream)."""
+        ev = self.__dict__.get("loss_ready")
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
 
     def train(self, epochs: int, log_every_pca: int = 25, log_every_probe: int = 10):
         """Layer-interleaved CD training (idbn.py:179-305).  ``loss_history`` receives the mean
@@ -175,6 +208,7 @@ class iDBN:
                 cur = nxt
             if cur is not None:
                 losses.extend(self.train_step(cur, epoch, epochs))
+            self.sync()
             if losses:
                 mean_loss = float(torch.stack(losses).mean())
                 self.loss_history.append(mean_loss)
