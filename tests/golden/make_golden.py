@@ -460,6 +460,32 @@ def case_imdbn():
     out["final_stream"] = stream
     save("imdbn", **out)
 
+    # ---- convergence traces of utils/conditional_steps.py on the trained model (one sample at a time,
+    # as the reference does); IMG->TXT draws one U[1,V] for the init, TXT->IMG draws nothing.
+    from imdbn.utils.conditional_steps import trace_img2txt_cross, trace_txt2img_cross
+    tr = dict(seed=JSEED, stream0=stream, n=4, max_steps=12)
+    for i in range(4):
+        PLAN.push("u", RandomField(JSEED, stream + i), 0)
+        a = trace_img2txt_cross(m, x[i:i + 1], y[i:i + 1], max_steps=12, eps_l1=1e-2, stable_steps=2,
+                                gap_thresh=0.05)
+        PLAN.done()
+        b = trace_txt2img_cross(m, x[i:i + 1], y[i:i + 1], max_steps=12, eps_z=5e-2, mse_tol=1e-4, patience=2)
+        tr[f"a{i}_steps"] = a["steps_to_converge"]; tr[f"a{i}_p_top1"] = np.array(a["p_top1"])
+        tr[f"a{i}_p_gap"] = np.array(a["p_gap"]); tr[f"a{i}_l1"] = np.array(a["l1"])
+        tr[f"a{i}_top1_idx"] = np.array(a["top1_idx"]); tr[f"a{i}_predT"] = a["predT"]
+        tr[f"a{i}_p_gt"] = np.array(a["p_gt"]); tr[f"a{i}_gt_idx"] = a["gt_idx"]
+        tr[f"b{i}_steps"] = b["steps_to_converge"]; tr[f"b{i}_z_l2"] = np.array(b["z_l2"])
+        tr[f"b{i}_image_mse"] = np.array(b["image_mse"]); tr[f"b{i}_best_mse"] = b["best_mse"]
+    for i, r in enumerate(m.image_idbn.layers):
+        tr.update(params_of(r, f"l{i}_"))
+    tr.update(params_of(jr, "joint_"))
+    tr["z_class_mean"] = m.z_class_mean.clone(); tr["x"] = x; tr["y"] = y
+    save("traces", **tr)
+
+    # ---- a checkpoint written by the reference itself (pickle of reference objects, CPU tensors):
+    # the drop-in must load it through the `imdbn` alias package
+    m.image_idbn.save_model(os.path.join(HERE, "ref_idbn.pkl"))
+
 
 if __name__ == "__main__":
     torch.set_num_threads(1)  # fixtures should not depend on the thread count of this machine

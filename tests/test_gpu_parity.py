@@ -370,3 +370,57 @@ def test_no_cpu_fallback(M):
         r.forward(torch.zeros(2, 8))
     with pytest.raises(RuntimeError):
         r.train_epoch(torch.zeros(2, 8), 0, 1)
+
+
+def test_conditional_steps_traces_golden(M, tmp_path, monkeypatch):
+    """utils/conditional_steps.py traces (reference: one sample at a time with .item() per step; here:
+    stepped on the device, convergence rule evaluated once) against the reference's own outputs."""
+    from multimodal_idbn_b200.conditional_steps import trace_img2txt_cross, trace_txt2img_cross, run_cross_panel
+    monkeypatch.chdir(tmp_path)
+    g = load_golden("traces")
+    x, y = T(g["x"]), T(g["y"])
+    m = M.iMDBN([40, 20, 10], 8, params=dict(PARAMS), dataloader=None, val_loader=None,
+                device=torch.device(DEV), num_labels=4)
+    for i, r in enumerate(m.image_idbn.layers):
+        load_params(r, g, f"l{i}_")
+    load_params(m.joint_rbm, g, "joint_")
+    m.z_class_mean = T(g["z_class_mean"]).to(DEV)
+    seed, s0 = int(g["seed"]), int(g["stream0"])
+    tol = dict(rtol=1e-3, atol=2e-5)
+    for i in range(int(g["n"])):
+        m.joint_rbm.set_rng(seed, s0 + i)
+        a = trace_img2txt_cross(m, x[i:i + 1], y[i:i + 1], max_steps=12, eps_l1=1e-2, stable_steps=2,
+                                gap_thresh=0.05)
+        assert a["steps_to_converge"] == int(g[f"a{i}_steps"]) and a["predT"] == int(g[f"a{i}_predT"])
+        assert a["top1_idx"] == [int(v) for v in g[f"a{i}_top1_idx"]] and a["gt_idx"] == int(g[f"a{i}_gt_idx"])
+        for key in ("p_top1", "p_gap", "l1", "p_gt"):
+            torch.testing.assert_close(torch.tensor(a[key]), T(g[f"a{i}_{key}"]).float(), **tol)
+        b = trace_txt2img_cross(m, x[i:i + 1], y[i:i + 1], max_steps=12, eps_z=5e-2, mse_tol=1e-4, patience=2)
+        assert b["steps_to_converge"] == int(g[f"b{i}_steps"])
+        torch.testing.assert_close(torch.tensor(b["z_l2"]), T(g[f"b{i}_z_l2"]).float(), **tol)
+        torch.testing.assert_close(torch.tensor(b["image_mse"]), T(g[f"b{i}_image_mse"]).float(), **tol)
+        assert abs(b["best_mse"] - float(g[f"b{i}_best_mse"])) < 1e-5
+    # the batched panel steps all samples together and must agree with the per-sample TXT->IMG traces
+    panel = run_cross_panel(m, x[:4], y[:4], max_steps=12, eps_z=5e-2, mse_tol=1e-4, patience=2)
+    assert panel["steps_txt2img"] == [int(g[f"b{i}_steps"]) for i in range(4)]
+
+
+def test_reference_checkpoint_loads_and_runs(M):
+    """A pickle written by the reference's own iDBN.save_model resolves to the CUDA-backed classes
+    through the `imdbn` alias package and runs after being moved to the GPU."""
+    import os
+    import pickle
+    from conftest import GOLDEN
+    with open(os.path.join(GOLDEN, "ref_idbn.pkl"), "rb") as f:
+        d = pickle.load(f)
+    assert set(d) == {"layers", "params"}
+    g = load_golden("traces")
+    x = T(g["x"]).reshape(g["x"].shape[0], -1).to(DEV)
+    v = x
+    for i, r in enumerate(d["layers"]):
+        assert type(r) is M.RBM
+        r.to(DEV)
+        torch.testing.assert_close(r.W.detach().cpu(), T(g[f"l{i}_W"]))
+        v = r.forward(v)
+    st = [O.RBMState(T(g[f"l{i}_W"]), T(g[f"l{i}_hb"]), T(g[f"l{i}_vb"]), None, None, None) for i in range(2)]
+    close(v, O.idbn_represent(st, x.cpu()))

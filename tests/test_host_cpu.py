@@ -170,3 +170,17 @@ def test_bench_reference_arm_prints_contract_line():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "samples/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_reference_pickle_resolves_to_drop_in_classes():
+    """tests/golden/ref_idbn.pkl was written by the reference's iDBN.save_model (reference objects)."""
+    import multimodal_idbn_b200 as M
+    with open(os.path.join(REPO, "tests", "golden", "ref_idbn.pkl"), "rb") as f:
+        d = pickle.load(f)
+    assert set(d) == {"layers", "params"} and len(d["layers"]) == 2
+    r = d["layers"][0]
+    assert type(r) is M.RBM and r.num_visible == 40 and r.num_hidden == 20
+    assert isinstance(r.W, torch.nn.Parameter) and r.W_m.shape == r.W.shape
+    assert not hasattr(r, "_rng_seed")                 # a reference object: no drop-in extras yet
+    r._next_rng()                                      # ...which the drop-in creates on first use
+    assert r._rng_stream == 1
