@@ -313,7 +313,7 @@ def chain_steps_metric(M, dev, n_chains, steps=50):
     vk2 = torch.zeros(n_chains, V, device=dev); km2 = torch.zeros_like(vk2); vk2[:, Dz:] = y; km2[:, Dz:] = 1
     mu = torch.rand(n_chains, Dz, device=dev)
     out = {"chains": n_chains, "steps": steps}
-    for name, fn in (("img2txt_cond_gibbs", lambda: r.conditional_gibbs(vk1, km1, n_steps=steps)),
+    for name, fn in (("img2txt_cond_gibbs", lambda: r.conditional_gibbs(vk1, km1, n_steps=steps, clamp_prefix=Dz)),
                      ("txt2img_noisy_mf", lambda: r.noisy_meanfield_annealed(vk2, km2, n_steps=steps))):
         r._mu_pull = {"mu_k": mu, "eta0": 0.15} if name.startswith("txt2img") else None
         fn(); torch.cuda.synchronize()

@@ -168,6 +168,9 @@ typedef struct {
     int32_t sample_h, sample_v;
     int32_t final_free_sweep; /* 1: return visible_probs(forward(v)) un-clamped (rbm.py:400) */
     uint32_t draw0;           /* first draw index used by this chain */
+    int32_t clamp_prefix;     /* >= 0: the caller promises known_mask == 1 exactly on columns
+                               * [0, clamp_prefix) and 0 elsewhere (enables the label-only fast path
+                               * of IMG->TXT inference); -1: arbitrary mask */
 } imdbn_chain;
 
 /* RBM.noisy_meanfield_annealed (rbm.py:300-367) / RBM.conditional_gibbs (rbm.py:369-400) /

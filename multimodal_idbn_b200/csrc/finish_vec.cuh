@@ -16,6 +16,10 @@ __device__ __forceinline__ float sigmoid_t(float x) {
     return sigmoidf_ref(x);
 }
 template <bool FAST>
+__device__ __forceinline__ float normal_t(const RngKey& k, uint32_t draw, uint32_t row, uint32_t col) {
+    return FAST ? rf_normal_fast(k, draw, row, col) : rf_normal(k, draw, row, col);
+}
+template <bool FAST>
 __device__ __forceinline__ float div_t(float x, float T, float invT) { return FAST ? x * invT : x / T; }
 
 __device__ __forceinline__ float4 sum_slabs4(const float* __restrict__ part, int ns, size_t stride, size_t i) {
@@ -56,7 +60,7 @@ k_finish_up4(const float* __restrict__ part, int splits, SKPlan sk, int B, int H
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             float x = div_t<FAST>(add_rn(a[e], bb[e]), T, invT);
-            if (sigma > 0.0f) x = add_rn(x, mul_rn(rf_normal(key, draw_n, b, j + e), sigma));
+            if (sigma > 0.0f) x = add_rn(x, mul_rn(normal_t<FAST>(key, draw_n, b, j + e), sigma));
             p[e] = sigmoid_t<FAST>(x);
             if (s_out) s[e] = (p[e] > rf_uniform(key, draw_u, b, j + e)) ? 1.0f : 0.0f;
         }
@@ -93,7 +97,7 @@ k_finish_down4(const float* __restrict__ part, int splits, SKPlan sk, int B, int
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             x[e] = div_t<FAST>(add_rn(a[e], bb[e]), T, invT);
-            if (sigma > 0.0f) x[e] = add_rn(x[e], mul_rn(rf_normal(key, draw_n, b, c + e), sigma));
+            if (sigma > 0.0f) x[e] = add_rn(x[e], mul_rn(normal_t<FAST>(key, draw_n, b, c + e), sigma));
         }
         if (!cp.enabled) {
 #pragma unroll

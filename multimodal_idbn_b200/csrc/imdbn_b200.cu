@@ -10,6 +10,7 @@
 #include "chain_kernel.cuh"
 #include "chain_stepped.cuh"
 #include "finish_vec.cuh"
+#include "label_gibbs.cuh"
 #include "tc_gemm.cuh"
 
 using namespace imdbn;
@@ -235,6 +236,15 @@ int launch_chain_r(imdbn_ctx* ctx, const ChainArgs& a, size_t smem, cudaStream_t
     return 0;
 }
 
+// IMG->TXT fast path (label_gibbs.cuh): mean-field conditional Gibbs, first Dz units clamped (caller's
+// promise), the rest = one softmax group of <= 32 units.
+bool chain_is_label_only(const imdbn_rbm* r, const imdbn_chain* ch, const float* vprob_out) {
+    return ch->kind == IMDBN_CHAIN_COND_GIBBS && !ch->sample_h && !ch->sample_v && !ch->v_init &&
+           r->ngroups == 1 && ch->clamp_prefix > 0 && ch->clamp_prefix == r->group_start[0] &&
+           r->group_end[0] == r->V && r->V - ch->clamp_prefix <= 32 && (r->H % 32) == 0 && r->H <= LG_MAXH &&
+           (ch->final_free_sweep || !vprob_out);
+}
+
 // Large mean-field batches in tf32 mode run the chain step by step on the tensor-core passes
 // (chain_stepped.cuh); everything else uses the persistent kernel.
 bool chain_is_stepped(const imdbn_ctx* ctx, const imdbn_rbm* r, const imdbn_chain* ch, int B) {
@@ -244,6 +254,10 @@ bool chain_is_stepped(const imdbn_ctx* ctx, const imdbn_rbm* r, const imdbn_chai
 
 size_t chain_ws_floats(const imdbn_ctx* ctx, const imdbn_rbm* r, const imdbn_chain* ch, int B) {
     size_t n = (size_t)r->V * r->H + 3 * (size_t)std::max(1, ch->n_steps) + 256;
+    if (chain_is_label_only(r, ch, nullptr)) {
+        const PassPlan pu = plan_pass(ctx, r, B, true), pd = plan_pass(ctx, r, B, false);
+        n += std::max(pu.part_floats, pd.part_floats) + 2 * (size_t)B * r->H + 4 * (size_t)B * r->V + 4096;
+    }
     if (chain_is_stepped(ctx, r, ch, B)) {
         const PassPlan pu = plan_pass(ctx, r, B, true), pd = plan_pass(ctx, r, B, false);
         n += std::max(pu.part_floats, pd.part_floats) + (size_t)B * r->H + 2 * (size_t)B * r->V + 1024;
@@ -312,11 +326,65 @@ int run_chain_stepped(imdbn_ctx* ctx, const imdbn_rbm* r, const imdbn_chain* ch,
     return 0;
 }
 
+int run_chain_label_only(imdbn_ctx* ctx, const imdbn_rbm* r, const imdbn_chain* ch, int B, float* v_out,
+                         float* vprob_out, const RngKey& key, cudaStream_t st) {
+    const int V = r->V, H = r->H, Dz = ch->clamp_prefix, K = V - Dz;
+    const PassPlan pu = plan_pass(ctx, r, B, true), pd = plan_pass(ctx, r, B, false);
+    float* part = arena_take<float>(ctx, std::max(pu.part_floats, pd.part_floats));
+    float* pre = arena_take<float>(ctx, (size_t)B * H);
+    float* hbuf = arena_take<float>(ctx, (size_t)B * H);
+    float* y = arena_take<float>(ctx, (size_t)B * K);
+    float* vz = arena_take<float>(ctx, (size_t)B * V);
+    float* lg_tmp = arena_take<float>(ctx, 2 * (size_t)B * V);
+    const dim3 gv((V + 255) / 256, std::min(B, 16384)), gh((H + 255) / 256, std::min(B, 16384));
+    // c = z W_z + b_h : one up-pass GEMM over [z | 0]
+    IMDBN_CUDA(ctx, cudaMemsetAsync(y, 0, (size_t)B * K * sizeof(float), st));
+    k_assemble_zy<<<gv, 256, 0, st>>>(ch->v_known, y, B, V, Dz, vz);
+    IMDBN_CHECK_LAUNCH(ctx, "k_assemble_zy");
+    int rc = gemm_up(ctx, r, vz, B, pu, part, st);
+    if (rc) return rc;
+    k_preact<<<gh, 256, 0, st>>>(part, pu.splits, pu.sk, B, H, r->hb, pre);
+    IMDBN_CHECK_LAUNCH(ctx, "k_preact");
+    LabelGibbsArgs a{};
+    a.pre = pre; a.Wy = r->W + (size_t)Dz * H; a.vby = r->vb + Dz;
+    a.B = B; a.H = H; a.K = K; a.Dz = Dz; a.n_steps = ch->n_steps;
+    a.key = key; a.draw0 = ch->draw0; a.y_out = y;
+    const size_t smem = ((size_t)64 * H + (size_t)LG_WARPS * LG_CHAINS * H) * sizeof(float);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_label_gibbs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    const int per_cta = LG_WARPS * LG_CHAINS;
+    const int blocks = std::max(1, std::min((B + per_cta - 1) / per_cta, ctx->num_sms * 2));
+    {
+        ProfScope prof(ctx, IMDBN_KERNEL_CHAIN, V, H, st);
+        k_label_gibbs<<<blocks, LG_WARPS * 32, smem, st>>>(a);
+        IMDBN_CHECK_LAUNCH(ctx, "k_label_gibbs");
+    }
+    if (!ch->final_free_sweep) {
+        k_assemble_zy<<<gv, 256, 0, st>>>(ch->v_known, y, B, V, Dz, v_out);
+        IMDBN_CHECK_LAUNCH(ctx, "k_assemble_zy");
+        return 0;
+    }
+    // the un-clamped sweep the reference returns: visible_probs(forward([z | y]))        rbm.py:400
+    k_assemble_zy<<<gv, 256, 0, st>>>(ch->v_known, y, B, V, Dz, vz);
+    IMDBN_CHECK_LAUNCH(ctx, "k_assemble_zy");
+    rc = up_pass(ctx, r, vz, B, 1.0f, hbuf, nullptr, key, 0, pu, part, st);
+    if (rc) return rc;
+    rc = down_pass(ctx, r, hbuf, B, 1.0f, v_out, nullptr, nullptr, lg_tmp, key, 0, 0, pd, part, st);
+    if (rc) return rc;
+    if (vprob_out)
+        IMDBN_CUDA(ctx, cudaMemcpyAsync(vprob_out, v_out, (size_t)B * V * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
 // Wt / tables must come from the arena of the current call.
 int run_chain(imdbn_ctx* ctx, const imdbn_rbm* r, const imdbn_chain* ch, int B, float* v_out,
               float* vprob_out, const RngKey& key, float* Wt, float* tables, cudaStream_t st) {
     IMDBN_ARG(ctx, ch->n_steps >= 0 && ch->n_steps <= CHAIN_MAX_STEPS);
     IMDBN_ARG(ctx, ch->v_known && ch->known_mask);
+    if (chain_is_label_only(r, ch, vprob_out)) return run_chain_label_only(ctx, r, ch, B, v_out, vprob_out, key, st);
     if (chain_is_stepped(ctx, r, ch, B)) return run_chain_stepped(ctx, r, ch, B, v_out, vprob_out, key, st);
     ChainArgs a{};
     a.W = r->W; a.Wt = Wt; a.hb = r->hb; a.vb = r->vb;

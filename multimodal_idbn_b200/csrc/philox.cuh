@@ -41,4 +41,13 @@ __device__ __forceinline__ float rf_normal(const RngKey& k, uint32_t draw, uint3
     return sqrtf(-2.0f * logf(u1)) * cosf(6.2831855f * u2);
 }
 
+// tf32-mode variant: hardware lg2 / cos approximations (absolute error ~1e-6, far below the tf32
+// operand rounding of the logits the noise is added to)
+__device__ __forceinline__ float rf_normal_fast(const RngKey& k, uint32_t draw, uint32_t row, uint32_t col) {
+    const uint4 x = philox4x32_10(col, row + k.row0, draw, k.stream, k.k0, k.k1);
+    const float u1 = ((float)(x.x >> 8) + 1.0f) * 5.9604644775390625e-8f;
+    const float u2 = (float)(x.y >> 8) * 5.9604644775390625e-8f;
+    return sqrtf(-2.0f * __logf(u1)) * __cosf(6.2831855f * u2);
+}
+
 }  // namespace imdbn

@@ -212,7 +212,7 @@ class iMDBN(nn.Module):
         v_known = torch.zeros(B, V, device=self.device)
         v_known[:, :Dz] = z_img
         v_i2t = jr.conditional_gibbs(v_known, self._block_mask(B, True), n_steps=steps,
-                                     sample_h=False, sample_v=False)
+                                     sample_h=False, sample_v=False, clamp_prefix=Dz)
         p_y_given_img = v_i2t[:, Dz:]
 
         v_known = torch.zeros(B, V, device=self.device)

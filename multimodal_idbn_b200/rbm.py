@@ -296,7 +296,7 @@ class RBM(nn.Module):
     # ------------------------------------------------------------------ conditional inference
     def _run_chain(self, kind, v_known, known_mask, n_steps, tables=None, mu=None, sample_h=False,
                    sample_v=False, final_free=False, v_init=None, draw0=0, rng=None,
-                   want_vprob=False):
+                   want_vprob=False, clamp_prefix=-1):
         vk = self._in(v_known, self.num_visible)
         km = self._in(known_mask, self.num_visible)
         if km.shape != vk.shape:
@@ -324,6 +324,7 @@ class RBM(nn.Module):
             ch.mu, ch.Dz = mu_t.data_ptr(), mu_t.shape[1]
         ch.sample_h, ch.sample_v, ch.final_free_sweep = int(sample_h), int(sample_v), int(final_free)
         ch.draw0 = draw0 & 0xFFFFFFFF
+        ch.clamp_prefix = int(clamp_prefix)
         out = torch.empty_like(vk)
         vprob = torch.empty_like(vk) if want_vprob else None
         rs = self._struct()
@@ -355,11 +356,16 @@ class RBM(nn.Module):
 
     @torch.no_grad()
     def conditional_gibbs(self, v_known: torch.Tensor, known_mask: torch.Tensor, n_steps: int = 30,
-                          sample_h: bool = False, sample_v: bool = False) -> torch.Tensor:
+                          sample_h: bool = False, sample_v: bool = False, *,
+                          clamp_prefix: int = -1) -> torch.Tensor:
         """n clamped sweeps then one un-clamped sweep, rbm.py:369-400.  Draws: 0 = U[B,V] init;
-        step t: 1+3t = U[B,H], 2+3t = U[B,V], 3+3t = categorical."""
+        step t: 1+3t = U[B,H], 2+3t = U[B,V], 3+3t = categorical.
+        ``clamp_prefix = Dz`` (keyword-only extension) is the caller's promise that ``known_mask`` is 1 on
+        exactly the first Dz columns: with a single trailing softmax group the chain then runs in the
+        label-only kernel (IMG->TXT inference of ``iMDBN._cross_reconstruct``)."""
         return self._run_chain(L.CHAIN_COND_GIBBS, v_known, known_mask, int(n_steps),
-                               sample_h=sample_h, sample_v=sample_v, final_free=True)
+                               sample_h=sample_h, sample_v=sample_v, final_free=True,
+                               clamp_prefix=clamp_prefix)
 
     @torch.no_grad()
     def conditional_gibbs_annealed(self, v_known: torch.Tensor, known_mask: torch.Tensor,

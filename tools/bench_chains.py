@@ -15,7 +15,7 @@ for B in [64, 4096, 65536]:
     vk = torch.zeros(B, V, device=dev); km = torch.zeros(B, V, device=dev); vk[:, :Dz] = z; km[:, :Dz] = 1
     vk2 = torch.zeros(B, V, device=dev); km2 = torch.zeros(B, V, device=dev); vk2[:, Dz:] = y; km2[:, Dz:] = 1
     mu = torch.rand(B, Dz, device=dev)
-    for name, fn in [("cond_gibbs(50)", lambda: r.conditional_gibbs(vk, km, n_steps=50)),
+    for name, fn in [("cond_gibbs(50)", lambda: r.conditional_gibbs(vk, km, n_steps=50, clamp_prefix=Dz)),
                      ("noisy_mf(50)", lambda: r.noisy_meanfield_annealed(vk2, km2, n_steps=50))]:
         r._mu_pull = {"mu_k": mu, "eta0": 0.15} if name.startswith("noisy") else None
         fn(); torch.cuda.synchronize()
