@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(NT) k_chain(ChainArgs a) {
         const bool free_sweep = (t == a.n_steps);
         const bool last = (t == total - 1);
         const float T = (noisy && !free_sweep) ? a.T[t] : 1.0f;
+        const float invT = 1.0f / T;
         const float sig = (noisy && !free_sweep) ? a.sigma[t] : 0.0f;
         uint32_t d_h, d_v, d_c;
         if (noisy) { d_h = a.draw0 + 1 + 2 * t; d_v = a.draw0 + 2 + 2 * t; d_c = 0; }
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(NT) k_chain(ChainArgs a) {
             const float bj = a.hb[j];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                float x = add_rn(acc[r], bj) / T;
+                float x = div_by(add_rn(acc[r], bj), T, invT);
                 if (sig > 0.0f) x = add_rn(x, mul_rn(rf_normal(a.key, d_h, row_base + r, j), sig));
                 float p = sigmoidf_ref(x);
                 if (a.sample_h && !free_sweep)
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(NT) k_chain(ChainArgs a) {
             const float bc = a.vb[c];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                float x = add_rn(acc[r], bc) / T;
+                float x = div_by(add_rn(acc[r], bc), T, invT);
                 if (sig > 0.0f) x = add_rn(x, mul_rn(rf_normal(a.key, d_v, row_base + r, c), sig));
                 lg[r * a.Vp + c] = x;
             }
@@ -220,7 +221,8 @@ __global__ void __launch_bounds__(NT) k_chain(ChainArgs a) {
             for (int c = s + lane; c < e; c += 32) sum += expf(L[c] - mx);
             for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
             __syncwarp();
-            for (int c = s + lane; c < e; c += 32) L[c] = expf(L[c] - mx) / sum;
+            const float rsum = 1.0f / sum;
+            for (int c = s + lane; c < e; c += 32) L[c] = div_by(expf(L[c] - mx), sum, rsum);
         }
         __syncthreads();
 
@@ -256,8 +258,9 @@ __global__ void __launch_bounds__(NT) k_chain(ChainArgs a) {
                 const float u = rf_uniform(a.key, d_c, row_base + r, g);
                 float cdf = 0.0f;
                 int idx = 0;
+                const float rtot = 1.0f / tot;
                 for (int c = s; c < e; ++c) {
-                    cdf += fminf(fmaxf(P[c], 1e-8f), 1.0f) / tot;
+                    cdf += div_by(fminf(fmaxf(P[c], 1e-8f), 1.0f), tot, rtot);
                     idx += (cdf <= u) ? 1 : 0;
                 }
                 idx = min(idx, e - s - 1);

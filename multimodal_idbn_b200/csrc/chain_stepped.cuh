@@ -35,10 +35,10 @@ __global__ void k_chain_up_finish(const float* __restrict__ part, int splits, SK
     if (j >= H) return;
     const int ns = finish_nslabs(sk, splits, j);
     const size_t n = (size_t)B * H;
-    const float bj = hb[j];
+    const float bj = hb[j], invT = 1.0f / T;
     for (int b = blockIdx.y; b < B; b += gridDim.y) {
         const size_t i = (size_t)b * H + j;
-        float x = add_rn(sum_slabs(part, ns, n, i), bj) / T;
+        float x = div_by(add_rn(sum_slabs(part, ns, n, i), bj), T, invT);
         if (sigma > 0.0f) x = add_rn(x, mul_rn(rf_normal(key, draw_n, b, j), sigma));
         h_out[i] = sigmoidf_ref(x);
     }
@@ -64,12 +64,12 @@ __global__ void k_chain_down_finish(const float* __restrict__ part, int splits, 
     if (c >= V) return;
     const int ns = finish_nslabs(sk, splits, c);
     const size_t n = (size_t)B * V;
-    const float bc = vb[c];
+    const float bc = vb[c], invT = 1.0f / T;
     bool in_group = false;
     for (int g = 0; g < po.gr.n; ++g) in_group |= (c >= po.gr.s[g] && c < po.gr.e[g]);
     for (int b = blockIdx.y; b < B; b += gridDim.y) {
         const size_t i = (size_t)b * V + c;
-        float x = add_rn(sum_slabs(part, ns, n, i), bc) / T;
+        float x = div_by(add_rn(sum_slabs(part, ns, n, i), bc), T, invT);
         if (sigma > 0.0f) x = add_rn(x, mul_rn(rf_normal(key, draw_n, b, c), sigma));
         if (in_group) { logits_out[i] = x; continue; }
         float p = sigmoidf_ref(x);
@@ -97,8 +97,9 @@ __global__ void k_chain_groups(const float* __restrict__ logits, int B, int V, C
     float sum = 0.0f;
     for (int c = s + lane; c < e; c += 32) sum += expf(logits[row + c] - mx);
     for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float rsum = 1.0f / sum;
     for (int c = s + lane; c < e; c += 32) {
-        float p = expf(logits[row + c] - mx) / sum;
+        float p = div_by(expf(logits[row + c] - mx), sum, rsum);
         if (po.mu && c < po.Dz)
             p = add_rn(mul_rn(1.0f - po.eta, p), mul_rn(po.eta, po.mu[(size_t)b * po.Dz + c]));
         if (po.vprob_out) po.vprob_out[row + c] = p;

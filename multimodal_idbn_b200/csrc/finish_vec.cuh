@@ -20,7 +20,7 @@ __device__ __forceinline__ float normal_t(const RngKey& k, uint32_t draw, uint32
     return FAST ? rf_normal_fast(k, draw, row, col) : rf_normal(k, draw, row, col);
 }
 template <bool FAST>
-__device__ __forceinline__ float div_t(float x, float T, float invT) { return FAST ? x * invT : x / T; }
+__device__ __forceinline__ float div_t(float x, float T, float invT) { return FAST ? x * invT : div_by(x, T, invT); }
 
 __device__ __forceinline__ float4 sum_slabs4(const float* __restrict__ part, int ns, size_t stride, size_t i) {
     float4 x = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(GTHREADS) k_gemm_ffma(GemmArgs g) {
             } else {
                 // W_m <- mom*W_m + lr*((S+ - S-)/bsz - wd*W);  W <- W + W_m   (rbm.py:212-213)
                 const float w = g.W[o];
-                const float grad = add_rn(acc[i][j] / g.bsz, -mul_rn(g.wd, w));
+                const float grad = add_rn(div_by(acc[i][j], g.bsz, 1.0f / g.bsz), -mul_rn(g.wd, w));
                 const float wm = add_rn(mul_rn(g.Wm[o], g.mom), mul_rn(g.lr, grad));
                 g.Wm[o] = wm;
                 g.W[o] = add_rn(w, wm);

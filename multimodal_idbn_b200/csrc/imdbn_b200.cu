@@ -352,14 +352,16 @@ int run_chain_label_only(imdbn_ctx* ctx, const imdbn_rbm* r, const imdbn_chain* 
     const size_t smem = ((size_t)64 * H + (size_t)LG_WARPS * LG_CHAINS * H) * sizeof(float);
     static size_t smem_set = 0;
     if (smem > smem_set) {
-        IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_label_gibbs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_label_gibbs<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_label_gibbs<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
     const int per_cta = LG_WARPS * LG_CHAINS;
     const int blocks = std::max(1, std::min((B + per_cta - 1) / per_cta, ctx->num_sms * 2));
     {
         ProfScope prof(ctx, IMDBN_KERNEL_CHAIN, V, H, st);
-        k_label_gibbs<<<blocks, LG_WARPS * 32, smem, st>>>(a);
+        if (ctx->precision == IMDBN_PREC_TF32) k_label_gibbs<true><<<blocks, LG_WARPS * 32, smem, st>>>(a);
+        else k_label_gibbs<false><<<blocks, LG_WARPS * 32, smem, st>>>(a);
         IMDBN_CHECK_LAUNCH(ctx, "k_label_gibbs");
     }
     if (!ch->final_free_sweep) {

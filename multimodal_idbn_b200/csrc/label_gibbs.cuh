@@ -24,6 +24,8 @@ struct LabelGibbsArgs {
     float* y_out;         // [B,K] label state after n_steps clamped sweeps
 };
 
+// FAST (tf32 mode): __expf / __fdividef sigmoid and softmax, 1e-6 relative, far inside the tf32 tolerance.
+template <bool FAST>
 __global__ void __launch_bounds__(LG_WARPS * 32) k_label_gibbs(LabelGibbsArgs a) {
     extern __shared__ __align__(16) float sm[];
     float* W = sm;                          // [K][H]
@@ -77,7 +79,9 @@ __global__ void __launch_bounds__(LG_WARPS * 32) k_label_gibbs(LabelGibbsArgs a)
             for (int q = 0; q < CH; ++q)
 #pragma unroll
                 for (int i = 0; i < NJ; ++i)
-                    if (i < nj) hw[q * a.H + lane + 32 * i] = sigmoidf_ref(acc[q][i]);
+                    if (i < nj)
+                        hw[q * a.H + lane + 32 * i] =
+                            FAST ? __fdividef(1.0f, 1.0f + __expf(-acc[q][i])) : sigmoidf_ref(acc[q][i]);
             __syncwarp();
             // logits_k = sum_j h_j W[k][j] + b_k  (lane = k), softmax over the warp   rbm.py:396, 113-114
             float lg[CH];
@@ -100,10 +104,10 @@ __global__ void __launch_bounds__(LG_WARPS * 32) k_label_gibbs(LabelGibbsArgs a)
             for (int q = 0; q < CH; ++q) {
                 float mx = lane < a.K ? lg[q] : -INFINITY;
                 for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                const float e = lane < a.K ? expf(lg[q] - mx) : 0.0f;
+                const float e = lane < a.K ? (FAST ? __expf(lg[q] - mx) : expf(lg[q] - mx)) : 0.0f;
                 float s = e;
                 for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                y[q] = e / s;
+                y[q] = FAST ? __fdividef(e, s) : div_by(e, s, 1.0f / s);
             }
         }
 #pragma unroll

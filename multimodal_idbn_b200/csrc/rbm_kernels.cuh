@@ -36,10 +36,10 @@ __global__ void k_finish_up(const float* __restrict__ part, int splits, SKPlan s
     if (j >= H) return;
     const int ns = finish_nslabs(sk, splits, j);
     const size_t n = (size_t)B * H;
-    const float bj = hb[j];
+    const float bj = hb[j], invT = 1.0f / T;
     for (int b = blockIdx.y; b < B; b += gridDim.y) {
         const size_t i = (size_t)b * H + j;
-        float x = add_rn(sum_slabs(part, ns, n, i), bj) / T;
+        float x = div_by(add_rn(sum_slabs(part, ns, n, i), bj), T, invT);
         const float p = sigmoidf_ref(x);
         if (p_out) p_out[i] = p;
         if (s_out) s_out[i] = (p > rf_uniform(key, draw_u, b, j)) ? 1.0f : 0.0f;
@@ -58,10 +58,10 @@ __global__ void k_finish_down(const float* __restrict__ part, int splits, SKPlan
     if (c >= V) return;
     const int ns = finish_nslabs(sk, splits, c);
     const size_t n = (size_t)B * V;
-    const float bc = vb[c];
+    const float bc = vb[c], invT = 1.0f / T;
     for (int b = blockIdx.y; b < B; b += gridDim.y) {
         const size_t i = (size_t)b * V + c;
-        float x = add_rn(sum_slabs(part, ns, n, i), bc) / T;
+        float x = div_by(add_rn(sum_slabs(part, ns, n, i), bc), T, invT);
         if (logits_out) logits_out[i] = x;
         const float p = sigmoidf_ref(x);
         if (p_out) p_out[i] = p;
@@ -101,7 +101,8 @@ __global__ void k_groups(const float* __restrict__ logits, float* __restrict__ p
         float sum = 0.0f;
         for (int c = s + lane; c < e; c += 32) sum += expf(logits[row + c] - mx);
         for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        for (int c = s + lane; c < e; c += 32) p[row + c] = expf(logits[row + c] - mx) / sum;
+        const float rsum = 1.0f / sum;
+        for (int c = s + lane; c < e; c += 32) p[row + c] = div_by(expf(logits[row + c] - mx), sum, rsum);
         __syncwarp();
     }
     if (s_out && lane == 0) {
@@ -110,8 +111,9 @@ __global__ void k_groups(const float* __restrict__ logits, float* __restrict__ p
         const float u = rf_uniform(key, draw_cat, b, g);
         float cdf = 0.0f;
         int idx = 0;
+        const float rtot = 1.0f / tot;
         for (int c = s; c < e; ++c) {
-            cdf += fminf(fmaxf(p[row + c], 1e-8f), 1.0f) / tot;
+            cdf += div_by(fminf(fmaxf(p[row + c], 1e-8f), 1.0f), tot, rtot);
             idx += (cdf <= u) ? 1 : 0;
         }
         idx = min(idx, e - s - 1);
@@ -246,10 +248,11 @@ __global__ void k_bias_update(float* __restrict__ st, const float* __restrict__ 
 // element-wise weight update from an (all-reduced) dS                          rbm.py:212-213
 __global__ void k_weight_update(const float* __restrict__ dS, size_t n, float* __restrict__ W,
                                 float* __restrict__ Wm, float lr, float mom, float wd, float bsz) {
+    const float rb = 1.0f / bsz;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
          i += (size_t)gridDim.x * blockDim.x) {
         const float w = W[i];
-        const float grad = add_rn(dS[i] / bsz, -mul_rn(wd, w));
+        const float grad = add_rn(div_by(dS[i], bsz, rb), -mul_rn(wd, w));
         const float wm = add_rn(mul_rn(Wm[i], mom), mul_rn(lr, grad));
         Wm[i] = wm;
         W[i] = add_rn(w, wm);

@@ -360,7 +360,7 @@ int tc_gemm_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* vp, const flo
     a.n_tiles = (r->H + ST_BN - 1) / ST_BN;
     a.k_chunks = (B + ST_KC - 1) / ST_KC;
     if (upd) { a.lr = upd->lr; a.mom = upd->momentum; a.wd = upd->weight_decay; a.bsz = (float)upd->batch_global; }
-    a.dbg = 0;
+    { static const int dbg_env = getenv("IMDBN_DEBUG_STATS") ? atoi(getenv("IMDBN_DEBUG_STATS")) : 0; a.dbg = dbg_env; }
     a.late_wait = ctx->stats_after_colstats ? 1 : 0;
     ctx->stats_after_colstats = false;
     a.w_policy = l2_policy_env("IMDBN_L2_W", L2_EVICT_NORMAL);

@@ -179,10 +179,17 @@ k_tc_stats(const __grid_constant__ CUtensorMap tmVP, const __grid_constant__ CUt
                         if (UPDATE) tma_store_2d_hint(&tmWm, n0 + qt * 32, m0, slot + ST_IO_BOX, a.wm_policy);
                     }
                     tma_store_commit();
-                    tma_store_wait_read();            // shared memory of the slot may be overwritten
-                    mbar_arrive(&io_empty[s]);
+                    if (a.dbg == 5) {
+                        // keep one store in flight: release the PREVIOUS slot once its store has drained
+                        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        if (hh > 0) mbar_arrive(&io_empty[(hh - 1) & (ST_NSLOT - 1)]);
+                    } else {
+                        tma_store_wait_read();        // shared memory of the slot may be overwritten
+                        mbar_arrive(&io_empty[s]);
+                    }
                 }
             }
+            if (a.dbg == 5 && hh > 0) { tma_store_wait_read(); mbar_arrive(&io_empty[(hh - 1) & (ST_NSLOT - 1)]); }
             tma_store_wait_all();                     // global writes complete before the kernel ends
         }
     } else {
@@ -222,6 +229,8 @@ k_tc_stats(const __grid_constant__ CUtensorMap tmVP, const __grid_constant__ CUt
                 if (a.dbg == 2) continue;
                 if (UPDATE && a.dbg != 4) mbar_wait(&io_full[s], (hh / ST_NSLOT) & 1);
                 else                      mbar_wait(&io_empty[s], ((hh / ST_NSLOT) & 1) ^ 1);
+                const float inv_bsz = 1.0f / a.bsz;
+                if (a.dbg != 6)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const uint32_t off = ((uint32_t)j ^ sw) << 4;
@@ -235,7 +244,7 @@ k_tc_stats(const __grid_constant__ CUtensorMap tmVP, const __grid_constant__ CUt
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             // W_m <- mom*W_m + lr*((S+ - S-)/bsz - wd*W);  W <- W + W_m
-                            const float g = add_rn(acc[4 * j + e] / a.bsz, -mul_rn(a.wd, wv[e]));
+                            const float g = add_rn(div_by(acc[4 * j + e], a.bsz, inv_bsz), -mul_rn(a.wd, wv[e]));
                             nm[e] = add_rn(mul_rn(mv[e], a.mom), mul_rn(a.lr, g));
                             nw[e] = add_rn(wv[e], nm[e]);
                         }
