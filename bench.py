@@ -208,16 +208,33 @@ def run_ours(args):
     # ---------------- end to end through the public API with host buffers: `e2e`
     loss_host = torch.empty(steps + warm, len(model.layers)).pin_memory()
 
+    rb_stream = torch.cuda.Stream(device=dev)                 # D2H read-back stream: never blocks the step stream
+
     def e2e_loop(n, off):
         loader = [(host[(off + i) % N_DISTINCT_BATCHES],) for i in range(n)]
         cur, i, pending = None, 0, None
         main = torch.cuda.current_stream(dev)
 
+        def finished(row, losses):                             # marks "step results are complete" on the step stream
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side = getattr(model, "loss_ready", None)           # set when upper layers run on a side stream
+            if side is not None:
+                rb_stream.wait_event(side)
+            return row, losses, ev
+
         def read_back(p):                                      # D2H read of a finished step's result
             row, losses, ev = p
-            if ev is not None:
-                main.wait_event(ev)                            # upper layers run on a side stream
-            loss_host[row].copy_(torch.stack(losses), non_blocking=True)
+            mode = os.environ.get("E2E_RB", "side")
+            if mode == "main":
+                loss_host[row].copy_(torch.stack(losses), non_blocking=True)
+                return
+            rb_stream.wait_event(ev)
+            with torch.cuda.stream(rb_stream):
+                loss_host[row].copy_(torch.stack(losses), non_blocking=True)
+            if mode != "nors":
+                for t in losses:
+                    t.record_stream(rb_stream)
 
         for b in M.prefetch_to_device(loader, dev):            # same lookahead loop as iDBN.train
             nxt = b[0]
@@ -225,14 +242,14 @@ def run_ours(args):
                 losses = model.train_step(cur, 0, 1, next_v=nxt)
                 if pending is not None:
                     read_back(pending)                         # step t-1 is read while step t is enqueued
-                pending = (off + i, losses, getattr(model, "loss_ready", None))
+                pending = finished(off + i, losses)
                 i += 1
             cur = nxt
         if cur is not None:
             losses = model.train_step(cur, 0, 1)
             if pending is not None:
                 read_back(pending)
-            pending = (off + i, losses, getattr(model, "loss_ready", None))
+            pending = finished(off + i, losses)
         if pending is not None:
             read_back(pending)
 

@@ -11,6 +11,7 @@
 #include "chain_stepped.cuh"
 #include "finish_vec.cuh"
 #include "label_gibbs.cuh"
+#include "cd_small.cuh"
 #include "tc_gemm.cuh"
 
 using namespace imdbn;
@@ -446,12 +447,92 @@ struct FwdTail {
     float* fwd_out;            // nullable [B + B_next, H]
 };
 
+// Small layers at small batch (the upper layers of an iDBN): the whole CD-k update + forward tail as ONE
+// persistent kernel (cd_small.cuh) instead of ~14 launches.
+static bool cd_small_eligible(const imdbn_ctx* ctx, const imdbn_rbm* r, const float* data, int B,
+                              const FwdTail* tail) {
+    // Measured on B200 (tools/bench_small.py, 1500 -> 500, batch 64): 63 us per call against 112 us for the
+    // fp32 multi-launch path and 84 us (host-bound) for the tf32 one; inside the C2 step, where the launches
+    // of the small layer are queued behind the 60 MB layer, the PDL-chained tcgen05 kernels are faster
+    // (about 48 us), so tf32 mode keeps them unless IMDBN_CD_SMALL=1.
+    static const bool off = getenv("IMDBN_NO_CD_SMALL") != nullptr;
+    static const bool force = getenv("IMDBN_CD_SMALL") != nullptr;
+    if (off || (ctx->precision != IMDBN_PREC_FP32 && !force)) return false;
+    if (r->ngroups != 0 || B > CDS_T || r->V % 4 || r->H % 4) return false;
+    if ((size_t)r->V * r->H > ((size_t)1 << 21)) return false;          // <= 8 MB of weights: L2-resident
+    if (!al16(data) || !al16(r->W) || !al16(r->Wm) || !al16(r->hb) || !al16(r->vb)) return false;
+    if (tail) {
+        if (tail->pos_h_in && !al16(tail->pos_h_in)) return false;
+        if (tail->next_data && (tail->B_next > CDS_T || tail->B_next <= 0 || !al16(tail->next_data))) return false;
+        if (tail->fwd_out && !al16(tail->fwd_out)) return false;
+    }
+    return ctx->num_sms >= 8;
+}
+
+static int cd_small(imdbn_ctx* ctx, const imdbn_rbm* r, const float* data, int B, int k,
+                    const imdbn_update* upd, const imdbn_rng* rng, float* loss_out, cudaStream_t st,
+                    const FwdTail* tail) {
+    const int V = r->V, H = r->H, G = ctx->num_sms;
+    CdSmallArgs a{};
+    a.W = r->W; a.Wm = r->Wm; a.hb = r->hb; a.hbm = r->hbm; a.vb = r->vb; a.vbm = r->vbm;
+    a.V = V; a.H = H; a.data = data; a.B = B; a.k = k;
+    if (tail) {
+        a.pos_h_in = tail->pos_h_in;
+        a.fwd_out = tail->fwd_out;
+        if (tail->fwd_out && tail->next_data) { a.next_data = tail->next_data; a.B_next = tail->B_next; }
+    }
+    a.lr = upd->lr; a.mom = upd->momentum; a.wd = upd->weight_decay; a.bsz = (float)upd->batch_global;
+    a.sparsity = upd->sparsity; a.sp_target = upd->sparsity_target;
+    a.loss_out = loss_out;
+    a.key = make_key(rng);
+    a.up = cds_plan(H, V, G); a.dn = cds_plan(V, H, G); a.fw = a.up;
+    const size_t nBH = (size_t)B * H, nBV = (size_t)B * V;
+    const size_t part_floats = std::max({(size_t)a.up.ksplit * nBH, (size_t)a.dn.ksplit * nBV,
+                                         (size_t)a.fw.ksplit * (size_t)(B + a.B_next) * H});
+    int rc = arena_begin(ctx, pad256(part_floats) + 3 * pad256(nBH) + 2 * pad256(nBV) + pad256(G), st);
+    if (rc) return rc;
+    a.part = arena_take<float>(ctx, part_floats);
+    a.pos_h = arena_take<float>(ctx, nBH);
+    a.h_s = arena_take<float>(ctx, nBH);
+    a.h_prob = arena_take<float>(ctx, nBH);
+    a.v_prob = arena_take<float>(ctx, nBV);
+    a.v_s = arena_take<float>(ctx, nBV);
+    a.sq_part = arena_take<float>(ctx, G);
+    a.bar = ctx->ticket + 8;
+    static const bool trace_on = getenv("IMDBN_CDS_TRACE") != nullptr;
+    static unsigned long long* trace_buf = nullptr;
+    if (trace_on && !trace_buf) cudaMalloc((void**)&trace_buf, 64 * sizeof(unsigned long long));
+    a.trace = trace_on ? trace_buf : nullptr;
+    static bool attr_set = false;
+    if (!attr_set) {
+        IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_cd_small, cudaFuncAttributeMaxDynamicSharedMemorySize, CDS_SMEM_BYTES));
+        attr_set = true;
+    }
+    ProfScope prof(ctx, IMDBN_KERNEL_STATS, V, H, st);
+    IMDBN_CUDA(ctx, launch_pdl(k_cd_small, dim3(G), dim3(CDS_THREADS), (size_t)CDS_SMEM_BYTES, st, a));
+    IMDBN_CHECK_LAUNCH(ctx, "k_cd_small");
+    if (trace_on) {
+        static int calls = 0;
+        if (++calls == 30) {
+            unsigned long long h[64];
+            cudaStreamSynchronize(st);
+            cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "cd_small phase trace (ns since start):");
+            for (int i = 1; i < 24; ++i) fprintf(stderr, " %lld", (long long)(h[i] - h[0]));
+            fprintf(stderr, "\n");
+        }
+    }
+    return 0;
+}
+
 int cd_core(imdbn_ctx* ctx, const imdbn_rbm* r, const float* data, int B, int k,
             const imdbn_update* upd, const imdbn_rng* rng, float* loss_out, float* stats_out,
             cudaStream_t st, const FwdTail* tail = nullptr) {
     int rc = check_rbm(ctx, r, stats_out == nullptr);
     if (rc) return rc;
     IMDBN_ARG(ctx, data && B > 0 && k >= 1 && rng);
+    if (!stats_out && upd && cd_small_eligible(ctx, r, data, B, tail))
+        return cd_small(ctx, r, data, B, k, upd, rng, loss_out, st, tail);
     const int V = r->V, H = r->H;
     const PassPlan pu = plan_pass(ctx, r, B, true), pd = plan_pass(ctx, r, B, false);
     const size_t nBH = (size_t)B * H, nBV = (size_t)B * V;
