@@ -148,18 +148,23 @@ class iDBN:
 
     # ------------------------------------------------------------------ training
     @torch.no_grad()
-    def train_step(self, v: torch.Tensor, epoch: int, epochs: int,
-                   next_v: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
+    def train_step(self, v: torch.Tensor, epoch: int, epochs: int, next_v: Optional[torch.Tensor] = None,
+                   loss_out: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
         """One minibatch of the hot loop (idbn.py:200-204); returns the per-layer losses as device
         scalars (no host synchronisation).  ``next_v`` = the next minibatch if already known (flattened
         fp32 on the device, the SAME tensor object that will be passed as ``v`` next time): the first
-        layer then computes its positive phase in this step's post-update forward pass."""
+        layer then computes its positive phase in this step's post-update forward pass.  ``loss_out`` =
+        optional fp32 vector with one element per layer (device or PINNED host memory) that the kernels
+        write the losses into directly; the returned list then holds views of it."""
         v = _flat(v, self.device)
+        if loss_out is not None and getattr(self, "pipeline_layers", False):
+            raise ValueError("loss_out is not supported together with pipeline_layers")
         if len(self.layers) == 1 or not getattr(self, "pipeline_layers", False) or v.device.type != "cuda":
             losses = []
             for i, rbm in enumerate(self.layers):
                 loss, v = rbm.train_epoch_fwd(v, epoch, epochs, CD=self.cd_k,
-                                              next_data=next_v if i == 0 else None)
+                                              next_data=next_v if i == 0 else None,
+                                              loss_out=None if loss_out is None else loss_out[i])
                 losses.append(loss)
             return losses
         # Optional (pipeline_layers = True; measured slower on B200 because the 197 KB tensor-core CTAs of the

@@ -236,20 +236,31 @@ class RBM(nn.Module):
 
     @torch.no_grad()
     def train_epoch_fwd(self, data: torch.Tensor, epoch: int, max_epochs: int, CD: int = 1,
-                        next_data: Optional[torch.Tensor] = None):
+                        next_data: Optional[torch.Tensor] = None, loss_out: Optional[torch.Tensor] = None):
         """``loss = train_epoch(data, ...); h = forward(data)`` as the iDBN training loop issues them
         (reference idbn.py:202-203), returned as ``(loss, h)``.  When ``next_data`` (the next minibatch of
         the same loader) is given, the forward pass also computes its positive hidden probabilities in the
         same pass over the updated ``W`` and keeps them for the next call, which then skips its first up
-        pass: one 4*V*H-byte stream of ``W`` less per minibatch, bit-identical results."""
+        pass: one 4*V*H-byte stream of ``W`` less per minibatch, bit-identical results.  ``loss_out`` = an
+        fp32 scalar the loss is written to by the kernel itself: a CUDA tensor, or PINNED host memory (the
+        device writes it over PCIe -- a device-to-host read-back without a copy operation in the stream)."""
         data = self._in(data, self.num_visible)
         if _dist.state() is not None:
-            return self.train_epoch(data, epoch, max_epochs, CD), self.forward(data)
+            loss = self.train_epoch(data, epoch, max_epochs, CD)
+            if loss_out is not None:
+                loss_out.copy_(loss, non_blocking=True)
+            return loss, self.forward(data)
         ctx, st = self._ctx()
         B = data.shape[0]
         lr, mom = self._hyper(epoch)
         rs = self._struct(training=True)
-        loss = torch.empty((), device=data.device, dtype=torch.float32)
+        if loss_out is None:
+            loss = torch.empty((), device=data.device, dtype=torch.float32)
+        else:
+            if loss_out.dtype != torch.float32 or loss_out.numel() != 1 or not (
+                    loss_out.is_cuda or loss_out.is_pinned()):
+                raise ValueError("loss_out must be one fp32 element on the device or in pinned host memory")
+            loss = loss_out
         rng = self._next_rng()
         upd = self._update_struct(lr, mom, B, self.sparsity)
         cached = self.__dict__.pop("_pos_cache", None)

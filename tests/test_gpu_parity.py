@@ -424,3 +424,23 @@ def test_reference_checkpoint_loads_and_runs(M):
         v = r.forward(v)
     st = [O.RBMState(T(g[f"l{i}_W"]), T(g[f"l{i}_hb"]), T(g[f"l{i}_vb"]), None, None, None) for i in range(2)]
     close(v, O.idbn_represent(st, x.cpu()))
+
+
+def test_train_step_writes_losses_into_pinned_host_memory(M, tmp_path, monkeypatch):
+    """loss_out: the update kernels store the per-layer losses straight into mapped pinned host memory."""
+    monkeypatch.chdir(tmp_path)
+    p = dict(LEARNING_RATE=0.1, WEIGHT_PENALTY=1e-4, INIT_MOMENTUM=0.5, FINAL_MOMENTUM=0.95, LEARNING_RATE_DYNAMIC=True)
+    x = [O.synthetic_images(16, 64, seed=s).to(DEV) for s in (1, 2)]
+    runs = []
+    for use_out in (False, True):
+        torch.manual_seed(0)
+        m = M.iDBN([64, 40, 24], dict(p), None, None, torch.device(DEV))
+        for l in m.layers:
+            l.set_rng(3, 0)
+        host = torch.full((2,), float("nan")).pin_memory()
+        ret = m.train_step(x[0], 0, 1, next_v=x[1], loss_out=host if use_out else None)
+        torch.cuda.synchronize()
+        runs.append(host.clone() if use_out else torch.stack(ret).cpu())
+    assert torch.isfinite(runs[1]).all() and torch.equal(runs[0], runs[1])
+    with pytest.raises(ValueError):
+        m.layers[0].train_epoch_fwd(x[0], 0, 1, loss_out=torch.zeros(1))        # pageable host memory
