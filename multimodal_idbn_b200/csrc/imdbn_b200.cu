@@ -59,9 +59,10 @@ PassPlan plan_pass(const imdbn_ctx* ctx, const imdbn_rbm* r, int B, bool up) {
 
 // part[s][B][H] = v[B,V] . W[V,H]   (K split over blockIdx.z)
 int gemm_up(imdbn_ctx* ctx, const imdbn_rbm* r, const float* v, int B, const PassPlan& pl,
-            float* part, cudaStream_t st) {
+            float* part, cudaStream_t st, const float* v2 = nullptr, int B1 = 0) {
     ProfScope prof(ctx, IMDBN_KERNEL_UP, r->V, r->H, st);
-    if (pl.sk.k_iters) return tc_gemm_up(ctx, r, v, B, part, st);
+    if (pl.sk.k_iters) return tc_gemm_up(ctx, r, v, B, part, st, v2, B1);
+    if (v2) return fail(ctx, -1, "two-source batches need the tensor-core path");
     GemmArgs g{};
     g.A = v; g.sAm = r->V; g.sAk = 1;
     g.B = r->W; g.sBk = r->H; g.sBn = 1;
@@ -124,8 +125,8 @@ inline bool vec_ok(int B, int N, const float* bias, const float* a, const float*
 
 int up_pass(imdbn_ctx* ctx, const imdbn_rbm* r, const float* v, int B, float T, float* p_out,
             float* s_out, const RngKey& key, uint32_t draw_u, const PassPlan& pl, float* part,
-            cudaStream_t st) {
-    int rc = gemm_up(ctx, r, v, B, pl, part, st);
+            cudaStream_t st, const float* v2 = nullptr, int B1 = 0) {
+    int rc = gemm_up(ctx, r, v, B, pl, part, st, v2, B1);
     if (rc) return rc;
     if (vec_ok(B, r->H, r->hb, p_out, s_out, nullptr)) {
         const size_t quads = (size_t)B * (r->H / 4);
@@ -588,6 +589,11 @@ int cd_core(imdbn_ctx* ctx, const imdbn_rbm* r, const float* data, int B, int k,
     if (rc || !do_fwd) return rc;
     // one pass over the updated W for [data ; next_data]
     const float* src = data;
+    if (Bt > B && pf.sk.k_iters && B % 8 == 0 && Bt <= 256) {
+        // tensor-core path: the TMA producer reads [data ; next_data] from the two matrices directly
+        float* part_f = arena_take<float>(ctx, pf.part_floats);
+        return up_pass(ctx, r, data, Bt, 1.0f, tail->fwd_out, nullptr, key, 0, pf, part_f, st, tail->next_data, B);
+    }
     if (Bt > B) {
         float* cat = arena_take<float>(ctx, (size_t)Bt * V);
         const size_t n1 = nBV / 4, n2 = (size_t)tail->B_next * V / 4;      // V % 4 == 0 on this path

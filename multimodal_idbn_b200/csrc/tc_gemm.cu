@@ -107,19 +107,22 @@ constexpr int TS_A_BYTES = TS_BM * TS_BK * 4;
 
 struct StreamArgs {
     int M_total, K_total, B, Npad;
+    int B1;                                // > 0: rows [0,B1) come from tmB, rows [B1,B) from tmB2 (two source matrices)
     SKPlan sk;
     int total_iters;
     float* part;                           // [slab][B][M_total]
     uint32_t tmem_cols;
     int stages;
     uint64_t w_policy;                     // L2 eviction priority of the W stream
+    unsigned long long* trace;             // nullable (IMDBN_TS_TRACE): [cta][8] globaltimer stamps
 };
 
 __host__ __device__ inline int ts_stage_bytes(int Npad) { return TS_A_BYTES + Npad * TS_BK * 4; }
 
 template <bool A_MN>
 __global__ void __launch_bounds__(TS_THREADS, 1)
-k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, StreamArgs a) {
+k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmB2, StreamArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stage_bytes = ts_stage_bytes(a.Npad);
@@ -135,11 +138,14 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int b0 = blockIdx.y * a.Npad;          // batches wider than 256 rows: one 256-row chunk per blockIdx.y
     const int beg = sk_beg(a.sk, cta), end = sk_beg(a.sk, cta + 1);
     const int k_iters = a.sk.k_iters;
+#define TS_MARK(i) do { if (a.trace) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.trace[(blockIdx.x + gridDim.x * blockIdx.y) * 8 + (i)] = t_; } } while (0)
 
     pdl_trigger();
+    if (threadIdx.x == 0) TS_MARK(0);
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        if (a.B1) tma_prefetch_desc(&tmB2);
         for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
         fence_barrier_init();
@@ -150,6 +156,7 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();                 // everything above overlapped the previous kernel's tail
+    if (threadIdx.x == 0) TS_MARK(1);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -172,8 +179,11 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         tma_load_2d_hint(sA + j * (TS_BM * 128), &tmA, k0 + j * 32, m0, &full[stage], a.w_policy);
                 }
 #pragma unroll
-                for (int j = 0; j < TS_BK / 32; ++j)
+                for (int j = 0; j < TS_BK / 32; ++j) {
                     tma_load_2d(sB + j * (a.Npad * 128), &tmB, k0 + j * 32, b0, &full[stage]);
+                    if (a.B1)      // second source matrix: its rows land behind the first one's (B1 % 8 == 0)
+                        tma_load_2d(sB + j * (a.Npad * 128) + a.B1 * 128, &tmB2, k0 + j * 32, 0, &full[stage]);
+                }
                 if (++stage == a.stages) { stage = 0; phase ^= 1; }
             }
         }
@@ -192,6 +202,7 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * a.Npad);
                 for (int i = 0; i < n_it; ++i) {
                     mbar_wait(&full[stage], phase);
+                    if (cur == beg && i == 0) TS_MARK(2);
                     tc_fence_after();
                     const uint32_t sA = smem_u32(smem + stage * stage_bytes);
                     const uint32_t sB = sA + TS_A_BYTES;
@@ -211,6 +222,7 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 mma_commit(&acc_full[buf]);
                 cur += n_it;
             }
+            TS_MARK(3);
         }
     } else {
         // ===================== epilogue: TMEM -> partial slab =====================
@@ -239,11 +251,13 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
             cur += n_it;
+            if (warp == 2 && lane == 0) TS_MARK(4 + min(seg, 1));
         }
     }
 
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) TS_MARK(6);
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, a.tmem_cols);
@@ -307,21 +321,22 @@ int tc_plan_max_slabs(const SKPlan& p, int M_total) {
 }
 
 template <bool A_MN>
-static int launch_stream(imdbn_ctx* ctx, const CUtensorMap* tmA, const CUtensorMap* tmB, StreamArgs& a, int G,
-                         int chunks, cudaStream_t st) {
+static int launch_stream(imdbn_ctx* ctx, const CUtensorMap* tmA, const CUtensorMap* tmB, const CUtensorMap* tmB2,
+                         StreamArgs& a, int G, int chunks, cudaStream_t st) {
     const size_t smem = (size_t)a.stages * ts_stage_bytes(a.Npad) + 1024 + 256;
     static size_t smem_set = 0;          // the attribute is sticky: raise it only when a larger size is needed
     if (smem > smem_set) {
         IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_tc_stream<A_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
-    IMDBN_CUDA(ctx, launch_pdl(k_tc_stream<A_MN>, dim3(G, chunks), dim3(TS_THREADS), smem, st, *tmA, *tmB, a));
+    IMDBN_CUDA(ctx, launch_pdl(k_tc_stream<A_MN>, dim3(G, chunks), dim3(TS_THREADS), smem, st, *tmA, *tmB, *tmB2, a));
     IMDBN_CHECK_LAUNCH(ctx, "k_tc_stream");
     return 0;
 }
 
+// act2 != nullptr: the batch is the virtual concatenation [act (B1 rows) ; act2 (B - B1 rows)]
 static int stream_pass(imdbn_ctx* ctx, const imdbn_rbm* r, const float* act, int B, float* part, bool up,
-                       cudaStream_t st) {
+                       cudaStream_t st, const float* act2 = nullptr, int B1 = 0) {
     const int M_total = up ? r->H : r->V, K_total = up ? r->V : r->H;
     if (!aligned16(act)) return fail(ctx, -1, "tc pass: activation pointer must be 16-byte aligned");
     StreamArgs a{};
@@ -336,14 +351,51 @@ static int stream_pass(imdbn_ctx* ctx, const imdbn_rbm* r, const float* act, int
     const int G = tc_plan_ctas(a.sk, M_total);
     // W is [V, H] row-major: inner = H.  up: boxes [64 k-rows x 32 h]; down: boxes [128 v-rows x 32 h]
     const CUtensorMap* tmA = get_map(ctx, r->W, r->H, r->V, up ? TS_BK : TS_BM, up);
-    const CUtensorMap* tmB = get_map(ctx, act, K_total, B, a.Npad, false);
-    if (!tmA || !tmB) return fail(ctx, -5, "cuTensorMapEncodeTiled failed");
-    return up ? launch_stream<true>(ctx, tmA, tmB, a, G, chunks, st)
-              : launch_stream<false>(ctx, tmA, tmB, a, G, chunks, st);
+    const CUtensorMap* tmB = nullptr;
+    const CUtensorMap* tmB2 = nullptr;
+    if (act2) {
+        if (B1 <= 0 || B1 % 8 || B1 >= B || B > 256 || !aligned16(act2))
+            return fail(ctx, -1, "tc pass: two-source batch needs B1 % 8 == 0, B <= 256");
+        a.B1 = B1;
+        tmB = get_map(ctx, act, K_total, B1, B1, false);                  // box = the B1 rows of the first source
+        tmB2 = get_map(ctx, act2, K_total, B - B1, a.Npad - B1, false);   // rows past B - B1 are zero-filled
+    } else {
+        tmB = get_map(ctx, act, K_total, B, a.Npad, false);
+        tmB2 = tmB;
+    }
+    if (!tmA || !tmB || !tmB2) return fail(ctx, -5, "cuTensorMapEncodeTiled failed");
+    // IMDBN_TS_TRACE=1: per-CTA globaltimer stamps of one large-layer launch (debug aid)
+    static const bool trace_on = getenv("IMDBN_TS_TRACE") != nullptr;
+    static unsigned long long* trace_buf = nullptr;
+    static int big_calls = 0;
+    const bool traced = trace_on && (size_t)r->V * r->H > (1u << 22) && ++big_calls >= 40 && big_calls <= 42;
+    if (traced) {
+        if (!trace_buf) cudaMalloc((void**)&trace_buf, 148 * 8 * 8);
+        cudaMemsetAsync(trace_buf, 0, 148 * 8 * 8, st);
+        a.trace = trace_buf;
+    }
+    int rc = up ? launch_stream<true>(ctx, tmA, tmB, tmB2, a, G, chunks, st)
+                : launch_stream<false>(ctx, tmA, tmB, tmB2, a, G, chunks, st);
+    if (traced && rc == 0) {
+        static unsigned long long h[148 * 8];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
+        unsigned long long t0 = ~0ull;
+        for (int c = 0; c < G; ++c) t0 = std::min(t0, h[c * 8]);
+        const char* names[7] = {"entry", "after pdl_wait", "first stage full", "last mma issued", "epilogue seg0", "epilogue seg1", "exit"};
+        fprintf(stderr, "k_tc_stream<%s> B=%d G=%d trace (ns after first CTA entry; min / mean / max over CTAs)\n", up ? "up" : "down", B, G);
+        for (int i = 0; i < 7; ++i) {
+            double mn = 1e18, mx = 0, sum = 0; int n = 0;
+            for (int c = 0; c < G; ++c) { if (!h[c * 8 + i]) continue; double v = (double)(h[c * 8 + i] - t0); mn = std::min(mn, v); mx = std::max(mx, v); sum += v; ++n; }
+            if (n) fprintf(stderr, "  %-18s %8.0f %8.0f %8.0f  (n=%d)\n", names[i], mn, sum / n, mx, n);
+        }
+    }
+    return rc;
 }
 
-int tc_gemm_up(imdbn_ctx* ctx, const imdbn_rbm* r, const float* v, int B, float* part, cudaStream_t st) {
-    return stream_pass(ctx, r, v, B, part, true, st);
+int tc_gemm_up(imdbn_ctx* ctx, const imdbn_rbm* r, const float* v, int B, float* part, cudaStream_t st,
+               const float* v2, int B1) {
+    return stream_pass(ctx, r, v, B, part, true, st, v2, B1);
 }
 int tc_gemm_down(imdbn_ctx* ctx, const imdbn_rbm* r, const float* h, int B, float* part, cudaStream_t st) {
     return stream_pass(ctx, r, h, B, part, false, st);

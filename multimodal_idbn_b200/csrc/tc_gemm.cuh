@@ -10,7 +10,9 @@ bool tc_down_supported(const imdbn_ctx* ctx, const imdbn_rbm* r, int B);
 bool tc_stats_supported(const imdbn_ctx* ctx, const imdbn_rbm* r, int B);
 size_t tc_ws_bytes(const imdbn_ctx* ctx, const imdbn_rbm* r, int B);
 
-int tc_gemm_up(imdbn_ctx* ctx, const imdbn_rbm* r, const float* v, int B, float* part, cudaStream_t st);
+// v2 != nullptr: the batch is [v (B1 rows) ; v2 (B - B1 rows)] read from two matrices (B1 % 8 == 0, B <= 256)
+int tc_gemm_up(imdbn_ctx* ctx, const imdbn_rbm* r, const float* v, int B, float* part, cudaStream_t st,
+               const float* v2 = nullptr, int B1 = 0);
 int tc_gemm_down(imdbn_ctx* ctx, const imdbn_rbm* r, const float* h, int B, float* part, cudaStream_t st);
 int tc_gemm_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* vp, const float* hp,
                   const float* vn, const float* hn, int B, float* dS_out, const imdbn_update* upd,
