@@ -183,6 +183,15 @@ def run_ours(args):
         td.all_reduce(t, op=td.ReduceOp.MAX)
         return float(t.item())
 
+    dp_desc = "single GPU"
+    if world > 1:
+        ds = M.dist.state()
+        if ds.p2p:
+            mc = ds.multicast
+            dp_desc = (f"dp{world} (batch-sharded; statistics exchanged over NVLink peer memory: reduce-scatter + slab update "
+                       f"+ all-gather in one kernel" + (", NVSwitch multimem reduce / broadcast when available)" if mc else ")"))
+        else:
+            dp_desc = f"dp{world} (batch-sharded, NCCL all-reduce of dS)"
     steps, warm = args.steps, args.warmup
     # ---------------- device-resident timing: `value`
     def batch(i):
@@ -265,7 +274,7 @@ def run_ours(args):
         "dtype": "f32" if args.precision == "fp32" else "tf32", "data": "synthetic",
         "config": {"workload": "C2 iDBN [10000,1500,500] CD-1 batch 64 per GPU (idbn.py:199-204)",
                    "global_batch": BATCH * world,
-                   "parallelism": f"dp{world} (batch-sharded, dS all-reduce)" if world > 1 else "single GPU",
+                   "parallelism": dp_desc,
                    "precision_mode": args.precision,
                    "l2": "state (W, W_m of both layers: 252 MB) + 164 MB of rotating inputs exceed the "
                          "126 MB L2; no explicit flush"},

@@ -138,11 +138,32 @@ int imdbn_cd_train_fwd(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* data, 
  *   stats_out = [ dS (V*H) | dh (H) | dv (V) | pos_h column sum (H) | squared error (1) ]
  * which the host all-reduces (NCCL) and hands to imdbn_apply_update on every rank. */
 int imdbn_cd_stats(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* data, int B, int k,
-                   const imdbn_rng* rng, float* stats_out, imdbn_stream stream);
+                   const imdbn_rng* rng, const float* pos_h_in /* nullable, as in imdbn_cd_train_fwd */,
+                   float* stats_out, imdbn_stream stream);
 int64_t imdbn_stats_size(const imdbn_rbm* rbm);
 /* rbm.py:211-226 on (all-reduced) statistics; n_elem_loss = global B*V for the loss mean. */
 int imdbn_apply_update(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* stats,
                        const imdbn_update* upd, float* loss_out, imdbn_stream stream);
+
+/* Data-parallel update over PEER MEMORY (NVLink / NVSwitch) -- replaces "all-reduce + imdbn_apply_update".
+ * Every rank has written its local statistics (imdbn_cd_stats / imdbn_cd_clamped_stats layout) into a buffer
+ * that is mapped into all ranks (CUDA IPC / symmetric memory), and every rank's W lives in such a buffer too.
+ * One kernel per rank: reduce-scatter of dS in rank order, rbm.py:212-213 on the rank's slab of W and W_m
+ * (W_m is only valid on its owner afterwards), all-gather of the new W into every rank's copy; the bias update
+ * and the loss (rbm.py:216-226) are computed redundantly on every rank from the rank-ordered sum of the small
+ * statistics.  The caller provides a cross-rank barrier BEFORE (all statistics written) and AFTER (all weights
+ * written, all statistics consumed) the call. */
+#define IMDBN_MAX_PEERS 8
+typedef struct {
+    int32_t world, rank;
+    const float* stats[IMDBN_MAX_PEERS]; /* rank i's statistics buffer, as mapped in THIS process */
+    float* W[IMDBN_MAX_PEERS];           /* rank i's W [V,H]; W[rank] == rbm->W */
+    const float* stats_mc;               /* nullable: NVSwitch multicast address of the statistics buffers --
+                                            the sum over ranks is then formed IN THE SWITCH (multimem.ld_reduce) */
+    float* W_mc;                         /* nullable: multicast address of the W buffers (multimem.st broadcast) */
+} imdbn_peers;
+int imdbn_dp_update(imdbn_ctx* ctx, const imdbn_rbm* rbm, const imdbn_peers* peers,
+                    const imdbn_update* upd, float* loss_out, imdbn_stream stream);
 
 /* The association statistics alone (rbm.py:200,209): dS_out [V,H] = vp^T hp - vn^T hn with
  * vp, vn [B,V] and hp, hn [B,H]. */

@@ -41,6 +41,15 @@ class UpdateStruct(C.Structure):
                 ("batch_global", C.c_int32)]
 
 
+MAX_PEERS = 8
+
+
+class PeersStruct(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32),
+                ("stats", C.c_void_p * MAX_PEERS), ("W", C.c_void_p * MAX_PEERS),
+                ("stats_mc", C.c_void_p), ("W_mc", C.c_void_p)]
+
+
 class ChainStruct(C.Structure):
     _fields_ = [("kind", C.c_int32), ("n_steps", C.c_int32),
                 ("v_known", C.c_void_p), ("known_mask", C.c_void_p), ("v_init", C.c_void_p),
@@ -79,9 +88,10 @@ SIGNATURES = {
                             C.POINTER(RngStruct), _P, _P]),
     "imdbn_cd_train_fwd": (_I, [_P, C.POINTER(RbmStruct), _P, _I, _I, C.POINTER(UpdateStruct),
                                 C.POINTER(RngStruct), _P, _P, _P, _I, _P, _P]),
-    "imdbn_cd_stats": (_I, [_P, C.POINTER(RbmStruct), _P, _I, _I, C.POINTER(RngStruct), _P, _P]),
+    "imdbn_cd_stats": (_I, [_P, C.POINTER(RbmStruct), _P, _I, _I, C.POINTER(RngStruct), _P, _P, _P]),
     "imdbn_stats_size": (C.c_int64, [C.POINTER(RbmStruct)]),
     "imdbn_apply_update": (_I, [_P, C.POINTER(RbmStruct), _P, C.POINTER(UpdateStruct), _P, _P]),
+    "imdbn_dp_update": (_I, [_P, C.POINTER(RbmStruct), C.POINTER(PeersStruct), C.POINTER(UpdateStruct), _P, _P]),
     "imdbn_assoc_stats": (_I, [_P, C.POINTER(RbmStruct), _P, _P, _P, _P, _I, _P, _P]),
     "imdbn_run_chain": (_I, [_P, C.POINTER(RbmStruct), C.POINTER(ChainStruct), _I, _P, _P,
                              C.POINTER(RngStruct), _P]),

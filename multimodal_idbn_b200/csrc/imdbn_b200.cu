@@ -12,6 +12,7 @@
 #include "finish_vec.cuh"
 #include "label_gibbs.cuh"
 #include "cd_small.cuh"
+#include "dp_update.cuh"
 #include "tc_gemm.cuh"
 
 using namespace imdbn;
@@ -889,9 +890,10 @@ int64_t imdbn_stats_size(const imdbn_rbm* r) {
 }
 
 int imdbn_cd_stats(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* data, int B, int k,
-                   const imdbn_rng* rng, float* stats_out, imdbn_stream stream) {
+                   const imdbn_rng* rng, const float* pos_h_in, float* stats_out, imdbn_stream stream) {
     IMDBN_ARG(ctx, stats_out != nullptr);
-    return cd_core(ctx, rbm, data, B, k, nullptr, rng, nullptr, stats_out, (cudaStream_t)stream);
+    FwdTail t{pos_h_in, nullptr, 0, nullptr};
+    return cd_core(ctx, rbm, data, B, k, nullptr, rng, nullptr, stats_out, (cudaStream_t)stream, pos_h_in ? &t : nullptr);
 }
 
 int imdbn_apply_update(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* stats,
@@ -906,6 +908,49 @@ int imdbn_apply_update(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* stats,
                                                                (float)upd->batch_global);
     IMDBN_CHECK_LAUNCH(ctx, "k_weight_update");
     return bias_update(ctx, rbm, const_cast<float*>(stats) + n, upd, (float)upd->batch_global * rbm->V, loss_out, st);
+}
+
+int imdbn_dp_update(imdbn_ctx* ctx, const imdbn_rbm* rbm, const imdbn_peers* peers,
+                    const imdbn_update* upd, float* loss_out, imdbn_stream stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_rbm(ctx, rbm, true);
+    if (rc) return rc;
+    IMDBN_ARG(ctx, peers && upd && upd->batch_global > 0);
+    IMDBN_ARG(ctx, peers->world >= 1 && peers->world <= IMDBN_MAX_PEERS && peers->rank >= 0 && peers->rank < peers->world);
+    const size_t n = (size_t)rbm->V * rbm->H;
+    IMDBN_ARG(ctx, n % 4 == 0 && al16(rbm->Wm) && peers->W[peers->rank] == rbm->W);
+    PeerPtrs p{};
+    p.world = peers->world;
+    for (int r = 0; r < peers->world; ++r) {
+        IMDBN_ARG(ctx, peers->stats[r] && peers->W[r] && al16(peers->stats[r]) && al16(peers->W[r]));
+        p.stats[r] = peers->stats[r];
+        p.W[r] = peers->W[r];
+    }
+    static const int dp_dbg = getenv("IMDBN_DP_DEBUG") ? atoi(getenv("IMDBN_DP_DEBUG")) : 0;   // timing experiments only
+    if (dp_dbg == 1) for (int r = 0; r < peers->world; ++r) p.W[r] = peers->W[peers->rank];        // no peer stores
+    if (dp_dbg == 2) for (int r = 0; r < peers->world; ++r) p.stats[r] = peers->stats[peers->rank]; // no peer loads
+    const int n_small = 2 * rbm->H + rbm->V + 1;
+    rc = arena_begin(ctx, pad256(n_small), st);
+    if (rc) return rc;
+    float* st_small = arena_take<float>(ctx, n_small);
+    k_dp_small<<<(n_small + 255) / 256, 256, 0, st>>>(p, n, n_small, st_small);
+    IMDBN_CHECK_LAUNCH(ctx, "k_dp_small");
+    const size_t nq = n / 4;
+    const size_t q0 = nq * (size_t)peers->rank / peers->world, q1 = nq * (size_t)(peers->rank + 1) / peers->world;
+    if (q1 > q0) {
+        const int blocks = (int)std::min<size_t>((q1 - q0 + 255) / 256, (size_t)ctx->num_sms * 8);
+        if (peers->stats_mc && peers->W_mc) {
+            IMDBN_ARG(ctx, al16(peers->stats_mc) && al16(peers->W_mc));
+            p.stats_mc = peers->stats_mc; p.W_mc = peers->W_mc;
+            k_dp_update<true><<<blocks, 256, 0, st>>>(p, peers->rank, q0, q1, rbm->Wm, upd->lr, upd->momentum,
+                                                      upd->weight_decay, (float)upd->batch_global);
+        } else {
+            k_dp_update<false><<<blocks, 256, 0, st>>>(p, peers->rank, q0, q1, rbm->Wm, upd->lr, upd->momentum,
+                                                       upd->weight_decay, (float)upd->batch_global);
+        }
+        IMDBN_CHECK_LAUNCH(ctx, "k_dp_update");
+    }
+    return bias_update(ctx, rbm, st_small, upd, (float)upd->batch_global * rbm->V, loss_out, st);
 }
 
 int imdbn_assoc_stats(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* vp, const float* hp,

@@ -244,7 +244,10 @@ class iDBN:
         return cur
 
     def save_model(self, path: str):
-        """``{"layers": [...], "params": ...}`` pickle (idbn.py:361-373)."""
+        """``{"layers": [...], "params": ...}`` pickle (idbn.py:361-373).  With peer-memory data parallelism
+        active this is a collective (every rank calls it; momenta slabs are gathered first)."""
+        for l in self.layers:
+            l.sync_momenta()
         with open(path, "wb") as f:
             pickle.dump({"layers": self.layers, "params": self.params}, f)
         print(f"[iDBN] Model saved to {path}")

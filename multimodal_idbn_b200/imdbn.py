@@ -336,6 +336,8 @@ class iMDBN(nn.Module):
         """Dual-format pickle (imdbn.py:815-883): DBN-compatible ``layers``/``params`` plus the full
         iMDBN components."""
         all_layers = list(self.image_idbn.layers) + [self.joint_rbm]
+        for l in all_layers:
+            l.sync_momenta()                 # no-op unless peer-memory data parallelism is active
         payload = {
             "layers": all_layers, "params": self.params,
             "image_idbn": self.image_idbn, "joint_rbm": self.joint_rbm,

@@ -213,10 +213,12 @@ class RBM(nn.Module):
         ctx, st = self._ctx()
         B = data.shape[0]
         lr, mom = self._hyper(epoch)
+        dp = _dist.state()
+        if dp is not None and dp.p2p:
+            self._p2p_setup(dp)                 # (collective, first call only) re-homes W in peer-mapped memory
         rs = self._struct(training=True)
         loss = torch.empty((), device=data.device, dtype=torch.float32)
         self._n_updates = getattr(self, "_n_updates", 0) + 1
-        dp = _dist.state()
         if dp is None:
             rng = self._next_rng()
             upd = self._update_struct(lr, mom, B, self.sparsity)
@@ -224,15 +226,72 @@ class RBM(nn.Module):
                                              C.byref(upd), C.byref(rng), L.ptr(loss), st),
                       "imdbn_cd_train")
             return loss
+        self._train_dp(dp, ctx, st, rs, data, B, CD, lr, mom, None, loss)
+        return loss
+
+    def _train_dp(self, dp, ctx, st, rs, data, B, CD, lr, mom, pos_in, loss) -> None:
+        """Sharded minibatch: local statistics -> cross-rank sum -> replicated update (dist.py)."""
         rng = self._next_rng(row0=dp.rank * B)
         stats = self._stats_buffer(ctx, rs)
         ctx.check(ctx.lib.imdbn_cd_stats(ctx.handle, C.byref(rs), L.ptr(data), B, int(CD),
-                                         C.byref(rng), L.ptr(stats), st), "imdbn_cd_stats")
-        dp.all_reduce(stats)
+                                         C.byref(rng), L.ptr(pos_in), L.ptr(stats), st), "imdbn_cd_stats")
         upd = self._update_struct(lr, mom, B * dp.world, self.sparsity)
-        ctx.check(ctx.lib.imdbn_apply_update(ctx.handle, C.byref(rs), L.ptr(stats), C.byref(upd),
-                                             L.ptr(loss), st), "imdbn_apply_update")
-        return loss
+        self._dp_apply(dp, ctx, rs, stats, upd, loss, st)
+
+    # ------------------------------------------------------------------ data parallelism
+    def _p2p_setup(self, dp):
+        """Peer-memory data parallelism (dist.py, csrc/dp_update.cuh): the statistics buffer and W live in
+        symmetric memory that every rank of the box can load from / store to over NVLink."""
+        st = self.__dict__.get("_p2p")
+        if st is not None and st["dp"] is dp and st["w_ptr"] == self.W.data_ptr():
+            return st
+        V, H = self.num_visible, self.num_hidden
+        if (V * H) % 4 or not self.W.is_cuda:
+            self._p2p = None                                     # falls back to the NCCL all-reduce
+            return None
+        S, hS = dp.symm_empty(V * H + 2 * H + V + 1)
+        Wflat, hW = dp.symm_empty(V * H)
+        Wsym = Wflat.view(V, H)
+        Wsym.copy_(self.W.data)
+        self.W.data = Wsym
+        peers = L.PeersStruct()
+        peers.world, peers.rank = dp.world, dp.rank
+        for r in range(dp.world):
+            peers.stats[r] = hS.buffer_ptrs[r]
+            peers.W[r] = hW.buffer_ptrs[r]
+        if dp.multicast:                                         # NVSwitch multicast objects (NVLS)
+            mcS, mcW = int(getattr(hS, "multicast_ptr", 0) or 0), int(getattr(hW, "multicast_ptr", 0) or 0)
+            if mcS and mcW:
+                peers.stats_mc, peers.W_mc = mcS, mcW
+        st = dict(dp=dp, w_ptr=self.W.data_ptr(), S=S, hS=hS, hW=hW, peers=peers)
+        self._p2p = st
+        hW.barrier(channel=0)                                    # every copy is in place before anyone stores into it
+        return st
+
+    def _dp_apply(self, dp, ctx, rs, stats, upd, loss, st) -> None:
+        """Make the local statistics global and apply the update on every rank (rbm.py:211-226)."""
+        p2p = self.__dict__.get("_p2p") if dp.p2p else None
+        if p2p is None:
+            dp.all_reduce(stats)
+            ctx.check(ctx.lib.imdbn_apply_update(ctx.handle, C.byref(rs), L.ptr(stats), C.byref(upd),
+                                                 L.ptr(loss), st), "imdbn_apply_update")
+            return
+        p2p["hS"].barrier(channel=0)                             # all ranks' statistics are complete
+        ctx.check(ctx.lib.imdbn_dp_update(ctx.handle, C.byref(rs), C.byref(p2p["peers"]), C.byref(upd),
+                                          L.ptr(loss), st), "imdbn_dp_update")
+        p2p["hS"].barrier(channel=1)                             # all slabs of W are in place everywhere
+
+    def sync_momenta(self) -> None:
+        """Peer-memory data parallelism keeps W_m only on the rank that owns each slab; this collective makes
+        it whole on every rank (call on ALL ranks, e.g. before saving or before ``dist.disable()``)."""
+        dp = _dist.state()
+        if dp is None or self.__dict__.get("_p2p") is None:
+            return
+        flat = self.W_m.view(-1)
+        q0, q1 = dp.slab(flat.numel() // 4)
+        flat[:4 * q0].zero_()
+        flat[4 * q1:].zero_()
+        dp.all_reduce(flat)
 
     @torch.no_grad()
     def train_epoch_fwd(self, data: torch.Tensor, epoch: int, max_epochs: int, CD: int = 1,
@@ -245,11 +304,9 @@ class RBM(nn.Module):
         fp32 scalar the loss is written to by the kernel itself: a CUDA tensor, or PINNED host memory (the
         device writes it over PCIe -- a device-to-host read-back without a copy operation in the stream)."""
         data = self._in(data, self.num_visible)
-        if _dist.state() is not None:
-            loss = self.train_epoch(data, epoch, max_epochs, CD)
-            if loss_out is not None:
-                loss_out.copy_(loss, non_blocking=True)
-            return loss, self.forward(data)
+        dp = _dist.state()
+        if dp is not None:
+            return self._train_epoch_fwd_dp(dp, data, epoch, CD, next_data, loss_out)
         ctx, st = self._ctx()
         B = data.shape[0]
         lr, mom = self._hyper(epoch)
@@ -282,12 +339,40 @@ class RBM(nn.Module):
             self._pos_cache = (self._pos_key(nxt), fwd[B:])
         return loss, fwd[:B]
 
+    def _train_epoch_fwd_dp(self, dp, data, epoch, CD, next_data, loss_out):
+        """``train_epoch_fwd`` on a sharded minibatch: the cached positive phase and the fused
+        forward-plus-next-positive pass work per shard exactly as on one GPU; only the update is global."""
+        ctx, st = self._ctx()
+        B = data.shape[0]
+        lr, mom = self._hyper(epoch)
+        if dp.p2p:
+            self._p2p_setup(dp)
+        rs = self._struct(training=True)
+        loss = torch.empty((), device=data.device, dtype=torch.float32)
+        cached = self.__dict__.pop("_pos_cache", None)
+        pos_in = None
+        if cached is not None and cached[0] == self._pos_key(data):
+            pos_in = cached[1]
+        self._train_dp(dp, ctx, st, rs, data, B, CD, lr, mom, pos_in, loss)
+        self._n_updates = getattr(self, "_n_updates", 0) + 1
+        if loss_out is not None:
+            loss_out.copy_(loss, non_blocking=True)
+        if next_data is None:
+            return loss, self.forward(data)
+        nxt = self._in(next_data, self.num_visible)
+        fwd = self.forward(torch.cat([data, nxt], 0))            # one pass over the updated W for both
+        self._pos_cache = (self._pos_key(nxt), fwd[B:])
+        return loss, fwd[:B]
+
     def _pos_key(self, x: torch.Tensor):
         """Identity of (input buffer, parameter state) under which cached positive probabilities hold."""
         return (x.data_ptr(), tuple(x.shape), x._version, self.W.data_ptr(), self.W._version,
                 self.hid_bias._version, getattr(self, "_n_updates", 0))
 
     def _stats_buffer(self, ctx, rs) -> torch.Tensor:
+        p2p = self.__dict__.get("_p2p")
+        if p2p is not None and _dist.state() is not None and _dist.state().p2p:
+            return p2p["S"]                                      # peer-mapped statistics buffer
         n = int(ctx.lib.imdbn_stats_size(C.byref(rs)))
         buf = getattr(self, "_stats_buf", None)
         if buf is None or buf.numel() != n or buf.device != self.W.device:
@@ -417,12 +502,14 @@ class RBM(nn.Module):
         ctx, st = self._ctx()
         B = vk.shape[0]
         lr, mom = self._hyper(epoch, aux_lr_mult)
+        dp = _dist.state()
+        if dp is not None and dp.p2p:
+            self._p2p_setup(dp)
         rs = self._struct(training=True)
         cfg = L.ClampedCfgStruct(int(CD), int(cond_init_steps), int(sample_h), int(sample_v),
                                  int(reclamp_negative), int(use_noisy_init))
         loss = torch.empty((), device=vk.device, dtype=torch.float32)
         self._n_updates = getattr(self, "_n_updates", 0) + 1
-        dp = _dist.state()
         if dp is None:
             rng = self._next_rng()
             upd = self._update_struct(lr, mom, B, False)
@@ -435,10 +522,8 @@ class RBM(nn.Module):
         ctx.check(ctx.lib.imdbn_cd_clamped_stats(ctx.handle, C.byref(rs), L.ptr(vk), L.ptr(km), B,
                                                  C.byref(cfg), C.byref(rng), L.ptr(stats), st),
                   "imdbn_cd_clamped_stats")
-        dp.all_reduce(stats)
         upd = self._update_struct(lr, mom, B * dp.world, False)
-        ctx.check(ctx.lib.imdbn_apply_update(ctx.handle, C.byref(rs), L.ptr(stats), C.byref(upd),
-                                             L.ptr(loss), st), "imdbn_apply_update")
+        self._dp_apply(dp, ctx, rs, stats, upd, loss, st)
         return loss
 
     # ------------------------------------------------------------------ pickling
@@ -446,6 +531,7 @@ class RBM(nn.Module):
         state = dict(self.__dict__)
         state.pop("_stats_buf", None)       # scratch, not model state
         state.pop("_pos_cache", None)
+        state.pop("_p2p", None)             # peer-memory handles
         return state
 
 

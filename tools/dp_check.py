@@ -31,11 +31,12 @@ ref = make()
 l1 = ref.train_epoch(data, 0, 1, CD=2)
 l2 = ref.train_epoch_clamped(vk, km, 0, 1, CD=1, cond_init_steps=10, sample_h=False)
 
-M.dist.enable()
+M.dist.enable(p2p={"1": True, "0": False}.get(os.environ.get("P2P", ""), None))
 lo, hi = M.dist.shard_rows(B, rank, world)
 r = make()
 d1 = r.train_epoch(data[lo:hi], 0, 1, CD=2)
 d2 = r.train_epoch_clamped(vk[lo:hi], km[lo:hi], 0, 1, CD=1, cond_init_steps=10, sample_h=False)
+r.sync_momenta()
 tol = dict(rtol=1e-4, atol=1e-6) if M.get_precision() == "fp32" else dict(rtol=1e-2, atol=1e-4)
 for a, b, n in ((r.W, ref.W, "W"), (r.hid_bias, ref.hid_bias, "hb"), (r.vis_bias, ref.vis_bias, "vb"),
                 (r.W_m, ref.W_m, "Wm"), (d1, l1, "loss"), (d2, l2, "loss_clamped")):
@@ -45,5 +46,6 @@ w = r.W.detach().clone(); td.broadcast(w, 0)
 assert torch.equal(w, r.W.detach())
 td.barrier()
 if rank == 0:
-    print(f"dp_check ok: world={world} precision={M.get_precision()}")
+    mc = bool(r.__dict__.get("_p2p") and r._p2p["peers"].stats_mc)
+    print(f"dp_check ok: world={world} precision={M.get_precision()} p2p={M.dist.state().p2p} multicast={mc}")
 td.destroy_process_group()
