@@ -127,6 +127,22 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel's layer-0 launch, from the committed
+    `ncu --set full` summary (profiles/r01_ncu_full_tc_stats.csv); None if the file is absent."""
+    import csv
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_full_tc_stats.csv")
+    try:
+        rows = list(csv.reader(open(path)))
+        h, units = rows[0], rows[1]
+        ir, iw, ig = h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum"), h.index("launch__grid_size")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        best = max((r for r in rows[2:] if r and "k_tc_stats" in r[1]), key=lambda r: float(r[ig]))
+        return float(best[ir]) * scale[units[ir]] + float(best[iw]) * scale[units[iw]]
+    except Exception:                                   # noqa: BLE001
+        return None
+
+
 def cpu_baseline(seconds_budget=15.0):
     from oracle import rbm_oracle as O
     from oracle.philox import RandomField
@@ -285,7 +301,7 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "layer-0 CD statistics + momentum/weight-decay update",
                      "achieved": ach, "peak": peak, "unit": "GB/s",
-                     "frac": (ach / peak) if ach else None, "traffic": None,
+                     "frac": (ach / peak) if ach else None, "traffic": ncu_traffic_bytes(),
                      "algorithmic_bytes_per_launch": upd_bytes, "peak_source": peak_src,
                      "avg_launch_ms": kern["stats_update"]["ms_avg"]},
         "kernels": {k: dict(v, gbs=(pass_bytes if k != "stats_update" else upd_bytes) /
