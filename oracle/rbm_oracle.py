@@ -506,6 +506,103 @@ def cross_reconstruct(layers: Sequence[RBMState], joint: RBMState, z_img, y_oneh
 # --------------------------------------------------------------------------------------------
 # synthetic data of the benchmark (SURVEY 8d / BASELINE.md 4.3)
 # --------------------------------------------------------------------------------------------
+# --------------------------------------------------------------------------------------------
+# iMDBN_BiModal (imdbn/models/imdbn_bimodal.py)
+# --------------------------------------------------------------------------------------------
+def bimodal_clamp(z: torch.Tensor, Dz1: int, Dz2: int, first: bool):
+    """(v_known, known_mask) with one modality clamped (imdbn_bimodal.py:655-660, 675-678)."""
+    B = z.shape[0]
+    vk = torch.zeros(B, Dz1 + Dz2, dtype=z.dtype)
+    km = torch.zeros_like(vk)
+    if first:
+        vk[:, :Dz1] = z; km[:, :Dz1] = 1.0
+    else:
+        vk[:, Dz1:] = z; km[:, Dz1:] = 1.0
+    return vk, km
+
+
+def bimodal_bias_init(joint0: RBMState, z1_batches, z2_batches, Dz1: int) -> None:
+    """imdbn_bimodal.py:617-646: vis_bias of the first joint layer = logit(mean latent) per modality."""
+    n = sum(z.shape[0] for z in z1_batches)
+    if n == 0:
+        return
+    s1 = z1_batches[0].sum(0)
+    for z in z1_batches[1:]:
+        s1 = s1 + z.sum(0)
+    s2 = z2_batches[0].sum(0)
+    for z in z2_batches[1:]:
+        s2 = s2 + z.sum(0)
+    m1 = (s1 / n).clamp(1e-4, 1 - 1e-4)
+    m2 = (s2 / n).clamp(1e-4, 1 - 1e-4)
+    joint0.vb[:Dz1] = torch.log(m1) - torch.log1p(-m1)
+    joint0.vb[Dz1:] = torch.log(m2) - torch.log1p(-m2)
+
+
+def bimodal_cross_reconstruct(mod1: Sequence[RBMState], mod2: Sequence[RBMState], joint0: RBMState, z1, z2,
+                              steps: int, seed: int, stream: int):
+    """imdbn_bimodal.py:648-694; consumes two call numbers of the first joint layer.
+    Returns (mod1_from_mod2, mod2_from_mod1)."""
+    Dz1, Dz2 = z1.shape[1], z2.shape[1]
+    vk, km = bimodal_clamp(z1, Dz1, Dz2, True)
+    z2_from_1 = conditional_gibbs(joint0, vk, km, n_steps=steps, sample_h=True, sample_v=False,
+                                  fld=RandomField(seed, stream))[:, Dz1:]
+    vk, km = bimodal_clamp(z2, Dz1, Dz2, False)
+    z1_from_2 = conditional_gibbs(joint0, vk, km, n_steps=steps, sample_h=True, sample_v=False,
+                                  fld=RandomField(seed, stream + 1))[:, :Dz1]
+    return idbn_decode(mod1, z1_from_2), idbn_decode(mod2, z2_from_1)
+
+
+def bimodal_train_joint(mod1: Sequence[RBMState], mod2: Sequence[RBMState], joint: Sequence[RBMState], batches,
+                        epochs: int, joint_cd: int, aux_steps: int, cross_steps: int, seeds: Sequence[int],
+                        bias_batches: int = 10, warmup_epochs: int = 8, streams: Optional[List[int]] = None):
+    """imdbn_bimodal.py:711-834 without the logging.  ``batches`` = list of (v1, v2) flattened fp32;
+    ``seeds[i]`` = random-field seed of joint layer i, every layer counting its calls from ``streams[i]``
+    (default 0).
+    Returns the per-epoch records {mod1_mse, mod2_mse, cd_loss}."""
+    z_of = lambda layers, v: idbn_represent(layers, v)
+    bimodal_bias_init(joint[0], [z_of(mod1, a) for a, _ in batches[:bias_batches]],
+                      [z_of(mod2, b) for _, b in batches[:bias_batches]], mod1[-1].H)
+    streams = list(streams) if streams is not None else [0] * len(joint)
+    Dz1, Dz2 = mod1[-1].H, mod2[-1].H
+    kw = dict(k=3, cond_init_steps=aux_steps, sample_h=True, sample_v=False, aux_lr_mult=0.3, use_noisy_init=True)
+
+    def clamped(vk, km, epoch, reclamp):
+        cd_train_clamped(joint[0], vk, km, epoch, reclamp_negative=reclamp,
+                         fld=RandomField(seeds[0], streams[0]), **kw)
+        streams[0] += 1
+
+    history = []
+    for epoch in range(epochs):
+        tot1 = tot2 = 0.0
+        n = 0
+        cd_losses = []
+        for v1, v2 in batches:
+            z1, z2 = z_of(mod1, v1), z_of(mod2, v2)
+            vk1, km1 = bimodal_clamp(z1, Dz1, Dz2, True)
+            vk2, km2 = bimodal_clamp(z2, Dz1, Dz2, False)
+            if epoch < warmup_epochs:
+                for _ in range(2):
+                    clamped(vk1, km1, epoch, True)
+                    clamped(vk2, km2, epoch, True)
+            else:
+                cur = torch.cat([z1, z2], 1)
+                for li, st in enumerate(joint):
+                    loss, _ = cd_train(st, cur, epoch, joint_cd, RandomField(seeds[li], streams[li]))
+                    streams[li] += 1
+                    if li == 0:
+                        cd_losses.append(float(loss))
+                    cur = hidden_probs(st, cur)
+                clamped(vk1, km1, epoch, False)
+                clamped(vk2, km2, epoch, False)
+            r1, r2 = bimodal_cross_reconstruct(mod1, mod2, joint[0], z1, z2, cross_steps, seeds[0], streams[0])
+            streams[0] += 2
+            tot1 += float(((r1 - v1) ** 2).sum()); tot2 += float(((r2 - v2) ** 2).sum())
+            n += v1.shape[0]
+        history.append(dict(mod1_mse=tot1 / (n * v1.shape[1]), mod2_mse=tot2 / (n * v2.shape[1]),
+                            cd_loss=float(np.mean(cd_losses)) if cd_losses else float("nan")))
+    return history
+
+
 def synthetic_images(n: int, d: int = 10000, p: float = 0.10, seed: int = 1234) -> torch.Tensor:
     g = torch.Generator(device="cpu").manual_seed(seed)
     return (torch.rand(n, d, generator=g) < p).float()

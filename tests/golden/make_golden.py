@@ -487,6 +487,77 @@ def case_imdbn():
     m.image_idbn.save_model(os.path.join(HERE, "ref_idbn.pkl"))
 
 
+def case_bimodal():
+    """iMDBN_BiModal (imdbn_bimodal.py): bias init, both cross directions with stochastic hidden units,
+    represent through a two-layer joint stack, and train_joint (8 warm-up + 2 main epochs x 2 batches)."""
+    import imdbn.models.imdbn_bimodal as ref_bi
+    assert ref_bi.RBM is RBM                      # the patched reference RBM
+    N, D1, D2 = 12, 36, 28
+    x1 = binary(N, D1, 111).view(N, 1, 6, 6)
+    x2 = binary(N, D2, 112, p=0.4).view(N, 1, 4, 7)
+    dl = _loader(x1, x2, 6)
+    params = dict(PARAMS, JOINT_CD=2, CROSS_GIBBS_STEPS=5, JOINT_AUX_COND_STEPS=4)
+    m = ref_bi.iMDBN_BiModal([D1, 20, 12], [D2, 16, 10], [14, 8], params=params, dataloader=dl, val_loader=dl,
+                             device=torch.device("cpu"))
+    _seed_idbn(m.mod1_dbn, 120)
+    _seed_idbn(m.mod2_dbn, 130)
+    for i, r in enumerate(m.joint_layers):
+        g = torch.Generator().manual_seed(140 + i)
+        with torch.no_grad():
+            r.W.copy_(torch.randn(r.num_visible, r.num_hidden, generator=g) * 0.5)
+            r.hid_bias.copy_(torch.randn(r.num_hidden, generator=g) * 0.2)
+    out = dict(x1=x1, x2=x2, seed=SEED, batch=6)
+    for name, dbn in (("m1", m.mod1_dbn), ("m2", m.mod2_dbn)):
+        for i, r in enumerate(dbn.layers):
+            out.update(params_of(r, f"in_{name}_l{i}_"))
+    for i, r in enumerate(m.joint_layers):
+        out.update(params_of(r, f"in_j{i}_"))
+    BSEED = SEED + 200                            # joint layer i uses seed BSEED + i, calls counted per layer
+    streams = [0, 0]
+
+    m.init_joint_bias_from_data(n_batches=2)
+    out["bias_vb"] = m.joint_layers[0].vis_bias.detach().clone()
+    out["represent"] = m.represent((x1, x2))
+
+    def plan_cross(steps):
+        for _ in range(2):
+            plan_cond_gibbs(RandomField(BSEED, streams[0]), steps, True, False, 0)
+            streams[0] += 1
+
+    z1 = m.mod1_dbn.represent(x1.view(N, -1)); z2 = m.mod2_dbn.represent(x2.view(N, -1))
+    plan_cross(5)
+    r1, r2 = m._cross_reconstruct(z1, z2, steps=5)
+    PLAN.done()
+    out["cross_mod1"] = r1; out["cross_mod2"] = r2
+
+    epochs, nb, aux = 10, 2, params["JOINT_AUX_COND_STEPS"]
+    for ep in range(epochs):
+        for b in range(nb):
+            if ep < 8:
+                for _ in range(4):
+                    plan_clamped(RandomField(BSEED, streams[0]), 3, aux, True, False, True, 0); streams[0] += 1
+            else:
+                for li in range(2):
+                    plan_cd(RandomField(BSEED + li, streams[li]), params["JOINT_CD"], 0); streams[li] += 1
+                for _ in range(2):
+                    plan_clamped(RandomField(BSEED, streams[0]), 3, aux, True, False, True, 0); streams[0] += 1
+            plan_cross(params["CROSS_GIBBS_STEPS"])
+    logged = []
+    m.wandb_run = types.SimpleNamespace(log=lambda d: logged.append(dict(d)))
+    m.val_loader = None                           # keeps the W&B plotting branches off
+    m.validation_mod1 = None                      # ... and the snapshot renderer (it would draw two more chains)
+    m.train_joint(epochs)
+    PLAN.done()
+    for i, r in enumerate(m.joint_layers):
+        out.update(params_of(r, f"out_j{i}_"))
+    out["train_epochs"] = epochs
+    out["final_streams"] = np.array(streams)
+    out["mod1_mse"] = np.array([d["cross_modality/mod1_mse"] for d in logged if "cross_modality/mod1_mse" in d])
+    out["mod2_mse"] = np.array([d["cross_modality/mod2_mse"] for d in logged if "cross_modality/mod2_mse" in d])
+    out["cd_loss"] = np.array([d["joint/cd_loss"] for d in logged if "joint/cd_loss" in d])
+    save("bimodal", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)  # fixtures should not depend on the thread count of this machine
     case_passes()
@@ -496,3 +567,4 @@ if __name__ == "__main__":
     case_clamped()
     case_idbn()
     case_imdbn()
+    case_bimodal()

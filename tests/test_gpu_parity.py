@@ -231,6 +231,53 @@ def test_imdbn_golden(M, tmp_path, monkeypatch):
     assert len(d["layers"]) == 3 and d["metadata"]["model_type"] == "iMDBN"
 
 
+def test_bimodal_golden(M, tmp_path, monkeypatch):
+    """iMDBN_BiModal drop-in against the reference's own run (tests/golden/bimodal.npz): bias init, represent
+    through the two-layer joint stack, both cross directions with stochastic hidden units, train_joint."""
+    monkeypatch.chdir(tmp_path)
+    g = load_golden("bimodal")
+    x1, x2 = T(g["x1"]), T(g["x2"])
+    dl = _loader(x1, x2, int(g["batch"]))
+    params = dict(PARAMS, JOINT_CD=2, CROSS_GIBBS_STEPS=5, JOINT_AUX_COND_STEPS=4)
+    m = M.iMDBN_BiModal([36, 20, 12], [28, 16, 10], [14, 8], params=params, dataloader=dl, val_loader=dl,
+                        device=torch.device(DEV))
+    assert m.arch_str == "MOD136-20-12_MOD228-16-10_JOINT14-8" and m.joint_rbm is m.joint_layers[0]
+    for name, dbn in (("m1", m.mod1_dbn), ("m2", m.mod2_dbn)):
+        for i, r in enumerate(dbn.layers):
+            load_params(r, g, f"in_{name}_l{i}_")
+    seed = int(g["seed"]) + 200
+    for i, r in enumerate(m.joint_layers):
+        load_params(r, g, f"in_j{i}_")
+        r.set_rng(seed + i, 0)
+    tol = dict(rtol=1e-4, atol=1e-5)
+    m.init_joint_bias_from_data(n_batches=2)
+    close(m.joint_layers[0].vis_bias, g["bias_vb"], tol)
+    close(m.represent((x1, x2)), g["represent"], tol)
+    z1 = m.mod1_dbn.represent(x1); z2 = m.mod2_dbn.represent(x2)
+    r1, r2 = m._cross_reconstruct(z1, z2, steps=5)
+    close(r1, g["cross_mod1"], tol); close(r2, g["cross_mod2"], tol)
+    assert m.joint_rbm._rng_stream == 2
+
+    m.train_joint(int(g["train_epochs"]))
+    assert [r._rng_stream for r in m.joint_layers] == [int(v) for v in g["final_streams"]]
+    for i, r in enumerate(m.joint_layers):     # ~100 dependent stochastic updates: looser tolerance
+        check_params(r, g, f"out_j{i}_", dict(rtol=5e-3, atol=5e-4))
+    hist = m.metrics_history
+    assert len(hist) == int(g["train_epochs"])
+    np.testing.assert_allclose([h["cross_modality/mod1_mse"] for h in hist], g["mod1_mse"], rtol=2e-3)
+    np.testing.assert_allclose([h["cross_modality/mod2_mse"] for h in hist], g["mod2_mse"], rtol=2e-3)
+    np.testing.assert_allclose([h["joint/cd_loss"] for h in hist if "joint/cd_loss" in h], g["cd_loss"], rtol=2e-3)
+
+    m.save_model(str(tmp_path / "b.pkl"))
+    d = M.iMDBN_BiModal.load_model(str(tmp_path / "b.pkl"), device=torch.device(DEV))
+    for key in ("mod1_dbn", "mod2_dbn", "joint_layers", "num_joint_layers", "Dz_mod1", "Dz_mod2", "params",
+                "arch_str", "features", "metadata"):
+        assert key in d
+    assert d["metadata"]["model_type"] == "iMDBN_BiModal" and len(d["joint_layers"]) == 2
+    assert b"multimodal_idbn_b200" not in open(tmp_path / "b.pkl", "rb").read()      # reference module paths
+    assert m.load_pretrained_mod1_dbn(str(tmp_path / "missing.pkl")) is False
+
+
 # ------------------------------------------------------------------------------ oracle at size
 def oracle_and_gpu(M, V, H, groups=None, seed=0, scale=1.0, **hyper):
     st = O.new_state(V, H, seed=seed, groups=groups, **hyper)

@@ -77,6 +77,13 @@ def test_no_cpu_fallback_and_reference_api_surface(tmp_path, monkeypatch):
     assert m2.joint_rbm.num_hidden == 4
     with pytest.raises(ValueError):
         M.iMDBN([20, 10], [5, 5], params=p)
+    from imdbn.models.imdbn_bimodal import iMDBN_BiModal
+    b = iMDBN_BiModal([36, 20, 12], [28, 16, 10], 14, params=p, device=torch.device("cpu"))
+    assert b is not None and iMDBN_BiModal is M.iMDBN_BiModal and b.num_joint_layers == 1
+    assert b.joint_rbm.num_visible == 22 and b.joint_rbm.softmax_groups == [] and b.arch_str.endswith("JOINT14")
+    for name in ("load_pretrained_mod1_dbn", "load_pretrained_mod2_dbn", "init_joint_bias_from_data",
+                 "_cross_reconstruct", "represent", "train_joint", "save_model", "load_model"):
+        assert callable(getattr(b, name))
 
 
 def test_pickle_layout_and_aliases(tmp_path, monkeypatch):

@@ -231,3 +231,44 @@ def test_imdbn_bias_init_cross_reconstruct_and_train_joint():
             _, stream = run_cross(layers, joint, zb, yb, zc, stream, seed, 6, False)
     assert stream == int(g["final_stream"])
     check_params(joint, g, "out_joint_")
+
+
+def bimodal_states(g):
+    mod1 = idbn_layers(g, "in_m1_")
+    mod2 = idbn_layers(g, "in_m2_")
+    joint = []
+    for i in range(2):
+        st = state_from(g, f"in_j{i}_")
+        st.lr, st.weight_decay, st.momentum, st.final_momentum, st.dynamic_lr = 0.04, 1e-4, 0.5, 0.95, True
+        joint.append(st)
+    return mod1, mod2, joint
+
+
+def test_bimodal_bias_init_cross_reconstruct_and_train_joint():
+    """iMDBN_BiModal (imdbn_bimodal.py:617-834) restated in the oracle against the reference's own run."""
+    g = load_golden("bimodal")
+    mod1, mod2, joint = bimodal_states(g)
+    x1 = T(g["x1"]).reshape(g["x1"].shape[0], -1)
+    x2 = T(g["x2"]).reshape(g["x2"].shape[0], -1)
+    bs, seed = int(g["batch"]), int(g["seed"]) + 200
+    batches = [(x1[i:i + bs], x2[i:i + bs]) for i in range(0, x1.shape[0], bs)]
+    O.bimodal_bias_init(joint[0], [O.idbn_represent(mod1, a) for a, _ in batches[:2]],
+                        [O.idbn_represent(mod2, b) for _, b in batches[:2]], 12)
+    torch.testing.assert_close(joint[0].vb, T(g["bias_vb"]), **TOL)
+    z1, z2 = O.idbn_represent(mod1, x1), O.idbn_represent(mod2, x2)
+    h = torch.cat([z1, z2], 1)
+    for st in joint:
+        h = O.hidden_probs(st, h)
+    torch.testing.assert_close(h, T(g["represent"]), **TOL)
+    r1, r2 = O.bimodal_cross_reconstruct(mod1, mod2, joint[0], z1, z2, 5, seed, 0)
+    torch.testing.assert_close(r1, T(g["cross_mod1"]), **TOL)
+    torch.testing.assert_close(r2, T(g["cross_mod2"]), **TOL)
+
+    # train_joint continues the call numbering of joint layer 0 after the two chains above
+    hist = O.bimodal_train_joint(mod1, mod2, joint, batches, int(g["train_epochs"]), joint_cd=2, aux_steps=4,
+                                 cross_steps=5, seeds=[seed, seed + 1], bias_batches=10, streams=[2, 0])
+    for i, st in enumerate(joint):
+        check_params(st, g, f"out_j{i}_")
+    np.testing.assert_allclose([h["mod1_mse"] for h in hist], g["mod1_mse"], rtol=1e-5)
+    np.testing.assert_allclose([h["mod2_mse"] for h in hist], g["mod2_mse"], rtol=1e-5)
+    np.testing.assert_allclose([h["cd_loss"] for h in hist if h["cd_loss"] == h["cd_loss"]], g["cd_loss"], rtol=1e-5)
