@@ -165,6 +165,17 @@ typedef struct {
 int imdbn_dp_update(imdbn_ctx* ctx, const imdbn_rbm* rbm, const imdbn_peers* peers,
                     const imdbn_update* upd, float* loss_out, imdbn_stream stream);
 
+/* IMG->TXT diagnostics with the image latents z [B,Dz] clamped and the remaining K = V - Dz visible units being
+ * the label group (utils/energy_utils.py):
+ *   class free energies (energy_utils.py:32-54): F_out[b][k] = F([z_b, e_k]) for every label k;
+ *   deterministic mean-field-lite trace (energy_utils.py:61-90 driven by :132-160): per step
+ *     h = sigmoid(zW_z + yW_y + b_h), s = sigmoid(hW_y^T + b_y), y = softmax(s); y_traj[t][b][:] = y after step
+ *     t+1; y_init nullable (uniform 1/K).  K <= 32, H % 32 == 0. */
+int imdbn_class_free_energies(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* z, int B, int Dz,
+                              float* F_out, imdbn_stream stream);
+int imdbn_trace_img2txt(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* z, int B, int Dz,
+                        const float* y_init, int steps, float* y_traj, imdbn_stream stream);
+
 /* The association statistics alone (rbm.py:200,209): dS_out [V,H] = vp^T hp - vn^T hn with
  * vp, vn [B,V] and hp, hn [B,H]. */
 int imdbn_assoc_stats(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* vp, const float* hp,

@@ -13,6 +13,7 @@
 #include "label_gibbs.cuh"
 #include "cd_small.cuh"
 #include "dp_update.cuh"
+#include "energy_diag.cuh"
 #include "tc_gemm.cuh"
 
 using namespace imdbn;
@@ -951,6 +952,79 @@ int imdbn_dp_update(imdbn_ctx* ctx, const imdbn_rbm* rbm, const imdbn_peers* pee
         IMDBN_CHECK_LAUNCH(ctx, "k_dp_update");
     }
     return bias_update(ctx, rbm, st_small, upd, (float)upd->batch_global * rbm->V, loss_out, st);
+}
+
+// ---- IMG->TXT diagnostics on the label-only structure (utils/energy_utils.py) --------------------------
+namespace {
+__global__ void k_pad_cols(const float* __restrict__ src, int B, int Dz, int V, float* __restrict__ dst) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= V) return;
+    for (int b = blockIdx.y; b < B; b += gridDim.y) dst[(size_t)b * V + c] = c < Dz ? src[(size_t)b * Dz + c] : 0.0f;
+}
+
+// pre = z W_z + b_h for a batch of latents z [B,Dz] (one up-pass GEMM over [z | 0])
+int label_preact(imdbn_ctx* ctx, const imdbn_rbm* r, const float* z, int B, int Dz, size_t extra_floats,
+                 float** pre_out, cudaStream_t st) {
+    const int V = r->V, H = r->H;
+    const PassPlan pu = plan_pass(ctx, r, B, true);
+    int rc = arena_begin(ctx, pad256(pu.part_floats) + pad256((size_t)B * V) + pad256((size_t)B * H) +
+                                  pad256(extra_floats), st);
+    if (rc) return rc;
+    float* part = arena_take<float>(ctx, pu.part_floats);
+    float* vz = arena_take<float>(ctx, (size_t)B * V);
+    float* pre = arena_take<float>(ctx, (size_t)B * H);
+    k_pad_cols<<<dim3((V + 255) / 256, std::min(B, 16384)), 256, 0, st>>>(z, B, Dz, V, vz);
+    IMDBN_CHECK_LAUNCH(ctx, "k_pad_cols");
+    rc = gemm_up(ctx, r, vz, B, pu, part, st);
+    if (rc) return rc;
+    k_preact<<<dim3((H + 255) / 256, std::min(B, 16384)), 256, 0, st>>>(part, pu.splits, pu.sk, B, H, r->hb, pre);
+    IMDBN_CHECK_LAUNCH(ctx, "k_preact");
+    *pre_out = pre;
+    return 0;
+}
+}  // namespace
+
+int imdbn_class_free_energies(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* z, int B, int Dz,
+                              float* F_out, imdbn_stream stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_rbm(ctx, rbm, false);
+    if (rc) return rc;
+    IMDBN_ARG(ctx, z && F_out && B > 0 && Dz > 0 && Dz < rbm->V);
+    const int K = rbm->V - Dz, H = rbm->H;
+    float* pre = nullptr;
+    rc = label_preact(ctx, rbm, z, B, Dz, 0, &pre, st);
+    if (rc) return rc;
+    k_class_free_energies<<<B, 256, H * sizeof(float), st>>>(pre, z, Dz, rbm->W + (size_t)Dz * H, rbm->vb, B, H, Dz, K,
+                                                            F_out);
+    IMDBN_CHECK_LAUNCH(ctx, "k_class_free_energies");
+    return 0;
+}
+
+int imdbn_trace_img2txt(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* z, int B, int Dz,
+                        const float* y_init, int steps, float* y_traj, imdbn_stream stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_rbm(ctx, rbm, false);
+    if (rc) return rc;
+    IMDBN_ARG(ctx, z && y_traj && B > 0 && steps > 0 && Dz > 0 && Dz < rbm->V);
+    const int K = rbm->V - Dz, H = rbm->H;
+    IMDBN_ARG(ctx, K <= 32 && H % 32 == 0);
+    const size_t smem = ((size_t)64 * H + (size_t)LG_WARPS * H) * sizeof(float);
+    IMDBN_ARG(ctx, smem <= 200 * 1024);
+    float* pre = nullptr;
+    rc = label_preact(ctx, rbm, z, B, Dz, 0, &pre, st);
+    if (rc) return rc;
+    TraceArgs a{};
+    a.pre = pre; a.Wy = rbm->W + (size_t)Dz * H; a.vby = rbm->vb + Dz; a.y_init = y_init;
+    a.B = B; a.H = H; a.K = K; a.steps = steps; a.y_traj = y_traj;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_trace_img2txt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    const int blocks = std::max(1, std::min((B + LG_WARPS - 1) / LG_WARPS, ctx->num_sms * 2));
+    k_trace_img2txt<<<blocks, LG_WARPS * 32, smem, st>>>(a);
+    IMDBN_CHECK_LAUNCH(ctx, "k_trace_img2txt");
+    return 0;
 }
 
 int imdbn_assoc_stats(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* vp, const float* hp,

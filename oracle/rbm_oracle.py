@@ -507,6 +507,64 @@ def cross_reconstruct(layers: Sequence[RBMState], joint: RBMState, z_img, y_oneh
 # synthetic data of the benchmark (SURVEY 8d / BASELINE.md 4.3)
 # --------------------------------------------------------------------------------------------
 # --------------------------------------------------------------------------------------------
+# IMG->TXT energy diagnostics (imdbn/utils/energy_utils.py)
+# --------------------------------------------------------------------------------------------
+def class_free_energies(joint: RBMState, z: torch.Tensor, K: int, Dz: int) -> torch.Tensor:
+    """F_k(z) = F([z, e_k]), [B,Dz] -> [B,K]  (energy_utils.py:32-54)."""
+    Wz, Wy = joint.W[:Dz], joint.W[Dz:Dz + K]
+    z_bz = (z * joint.vb[:Dz].unsqueeze(0)).sum(dim=1, keepdim=True)
+    pre = (z @ Wz + joint.hb.unsqueeze(0)).unsqueeze(1) + Wy.unsqueeze(0)
+    return -(z_bz + joint.vb[Dz:Dz + K].unsqueeze(0)) - torch.nn.functional.softplus(pre).sum(dim=2)
+
+
+def img2txt_lite_step(joint: RBMState, v: torch.Tensor, Dz: int, K: int) -> torch.Tensor:
+    """energy_utils.py:61-90 in its deterministic configuration: plain sigmoids, z re-clamped, y = softmax of
+    the SIGMOID outputs of the label units."""
+    h = torch.sigmoid(v @ joint.W + joint.hb)
+    v_next = torch.sigmoid(h @ joint.W.T + joint.vb)
+    v_next[:, :Dz] = v[:, :Dz]
+    v_next[:, Dz:Dz + K] = torch.softmax(v_next[:, Dz:Dz + K], dim=1)
+    return v_next
+
+
+def trace_single_img2txt(layers: Sequence[RBMState], joint: RBMState, x: torch.Tensor, gt: Optional[int], K: int,
+                         steps: int = 30, eps_l1: float = 1e-3, stable_steps: int = 3, gap_thresh: float = 0.25):
+    """energy_utils.py:96-196 for one flattened image x [1,D]."""
+    z = idbn_represent(layers, x).clamp(1e-6, 1 - 1e-6)
+    Dz = z.shape[1]
+    Fk = class_free_energies(joint, z, K, Dz).squeeze(0)
+    kstar = int(torch.argmin(Fk))
+    Fmin = Fk[kstar]
+    top2 = torch.topk(Fk, k=2, largest=False).values
+    out = dict(margin_energy=float(top2[1] - top2[0]), kstar=kstar, gt=gt, p_top1=[], p_top2=[], p_gap=[], p_gt=[],
+               deltaF_pred_traj=[])
+    y = torch.full((1, K), 1.0 / K)
+    v = torch.cat([z, y], dim=1)
+    y_prev, pred_cur, streak, conv = y.clone(), int(y.argmax(dim=1)), 0, steps + 1
+    for t in range(1, steps + 1):
+        v = img2txt_lite_step(joint, v, Dz, K)
+        y = v[:, Dz:Dz + K]
+        vals, _ = y.topk(2, dim=1)
+        p1, p2 = float(vals[0, 0]), float(vals[0, 1])
+        out["p_top1"].append(p1); out["p_top2"].append(p2); out["p_gap"].append(p1 - p2)
+        if gt is not None:
+            out["p_gt"].append(float(y[0, gt]))
+        pred_new = int(y.argmax(dim=1))
+        streak = streak + 1 if pred_new == pred_cur else 1
+        pred_cur = pred_new
+        out["deltaF_pred_traj"].append(float(Fk[pred_cur] - Fmin))
+        l1 = float((y - y_prev).abs().sum())
+        if l1 < eps_l1 and streak >= stable_steps and (pred_cur == kstar or (p1 - p2) >= gap_thresh):
+            conv = t
+            break
+        y_prev = y.clone()
+    fe = torch.softmax(-Fk, dim=0)
+    t2 = fe.topk(2).values
+    out.update(steps_to_converge=conv, predT=pred_cur, fe_top1_final=float(fe.max()), fe_gap_final=float(t2[0] - t2[1]))
+    return out
+
+
+# --------------------------------------------------------------------------------------------
 # iMDBN_BiModal (imdbn/models/imdbn_bimodal.py)
 # --------------------------------------------------------------------------------------------
 def bimodal_clamp(z: torch.Tensor, Dz1: int, Dz2: int, first: bool):

@@ -487,6 +487,38 @@ def case_imdbn():
     m.image_idbn.save_model(os.path.join(HERE, "ref_idbn.pkl"))
 
 
+def case_energy():
+    """utils/energy_utils.py: class_free_energies for a batch and trace_single_img2txt for four cases on a
+    seeded (untrained) iMDBN whose joint RBM has H = 32 hidden units."""
+    from imdbn.utils.energy_utils import class_free_energies, trace_single_img2txt
+    N, D, K = 12, 40, 4
+    x = binary(N, D, 151).view(N, 1, 5, 8)
+    y = onehot(N, K, 152)
+    dl = _loader(x, y, 6)
+    m = ref_imdbn_mod.iMDBN([D, 20, 12], 32, params=dict(PARAMS), dataloader=dl, val_loader=dl,
+                            device=torch.device("cpu"), num_labels=K)
+    _seed_idbn(m.image_idbn, 160)
+    jr = m.joint_rbm
+    g = torch.Generator().manual_seed(170)
+    with torch.no_grad():
+        jr.W.copy_(torch.randn(jr.num_visible, jr.num_hidden, generator=g) * 0.8)
+        jr.hid_bias.copy_(torch.randn(jr.num_hidden, generator=g) * 0.3)
+        jr.vis_bias.copy_(torch.randn(jr.num_visible, generator=g) * 0.3)
+    out = dict(x=x, y=y, K=K)
+    for i, r in enumerate(m.image_idbn.layers):
+        out.update(params_of(r, f"l{i}_"))
+    out.update(params_of(jr, "joint_"))
+    z = m.image_idbn.represent(x)
+    out["Fk"] = class_free_energies(jr, z, K, 12)
+    for i in range(4):
+        tr = trace_single_img2txt(m, x[i:i + 1], y[i:i + 1], steps=12, eps_l1=1e-4, stable_steps=3, gap_thresh=0.9)
+        for key in ("p_top1", "p_top2", "p_gap", "p_gt", "deltaF_pred_traj"):
+            out[f"t{i}_{key}"] = np.array(tr[key])
+        for key in ("steps_to_converge", "kstar", "predT", "margin_energy", "fe_top1_final", "fe_gap_final", "gt"):
+            out[f"t{i}_{key}"] = tr[key]
+    save("energy", **out)
+
+
 def case_bimodal():
     """iMDBN_BiModal (imdbn_bimodal.py): bias init, both cross directions with stochastic hidden units,
     represent through a two-layer joint stack, and train_joint (8 warm-up + 2 main epochs x 2 batches)."""
@@ -568,3 +600,4 @@ if __name__ == "__main__":
     case_idbn()
     case_imdbn()
     case_bimodal()
+    case_energy()

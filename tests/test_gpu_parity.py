@@ -278,6 +278,55 @@ def test_bimodal_golden(M, tmp_path, monkeypatch):
     assert m.load_pretrained_mod1_dbn(str(tmp_path / "missing.pkl")) is False
 
 
+def test_energy_diagnostics_golden_and_at_size(M, tmp_path, monkeypatch):
+    """utils/energy_utils.py drop-in: class free energies and the IMG->TXT trace against the reference's own
+    run (tests/golden/energy.npz), then against the oracle at the C3 joint shape (500 + 32 -> 256)."""
+    monkeypatch.chdir(tmp_path)
+    from imdbn.utils import energy_utils as E
+    g = load_golden("energy")
+    K = int(g["K"])
+    x, y = T(g["x"]), T(g["y"])
+    dl = _loader(x, y, 6)
+    m = M.iMDBN([40, 20, 12], 32, params=dict(PARAMS), dataloader=dl, val_loader=dl, device=torch.device(DEV),
+                num_labels=K)
+    for i, r in enumerate(m.image_idbn.layers):
+        load_params(r, g, f"l{i}_")
+    load_params(m.joint_rbm, g, "joint_")
+    z = m.image_idbn.represent(x)
+    close(E.class_free_energies(m.joint_rbm, z, K, 12), g["Fk"], dict(rtol=1e-5, atol=2e-5))
+    keys_l = ("p_top1", "p_top2", "p_gap", "p_gt", "deltaF_pred_traj")
+    keys_s = ("steps_to_converge", "kstar", "predT", "margin_energy", "fe_top1_final", "fe_gap_final", "gt")
+    batch = E.trace_batch_img2txt(m, x[:4], y[:4], steps=12, eps_l1=1e-4, stable_steps=3, gap_thresh=0.9)
+    for i in range(4):
+        single = E.trace_single_img2txt(m, x[i:i + 1], y[i:i + 1], steps=12, eps_l1=1e-4, stable_steps=3, gap_thresh=0.9)
+        for tr in (single, batch[i]):
+            for key in keys_l:
+                np.testing.assert_allclose(tr[key], g[f"t{i}_{key}"], rtol=1e-5, atol=2e-6, err_msg=key)
+            for key in keys_s:
+                np.testing.assert_allclose(tr[key], g[f"t{i}_{key}"], rtol=1e-4, atol=2e-5, err_msg=key)
+    # one deterministic step through the public helper
+    v = torch.cat([z, torch.full((z.size(0), K), 1.0 / K, device=DEV)], 1)
+    st_joint = O.RBMState(T(g["joint_W"]), T(g["joint_hb"]), T(g["joint_vb"]), T(g["joint_Wm"]), T(g["joint_hbm"]),
+                          T(g["joint_vbm"]), groups=[(12, 12 + K)])
+    close(E._deterministic_img2txt_step(m.joint_rbm, v, 12, K), O.img2txt_lite_step(st_joint, v.cpu(), 12, K),
+          dict(rtol=1e-5, atol=2e-6))
+    img, lbl = E.pick_fixed_val_case(m, target_label=int(y[3].argmax()))
+    assert img.shape[0] == 1 and int(lbl.argmax()) == int(y[3].argmax()) and m._fixed_val_case is not None
+
+    # C3 joint shape, 300 cases, against the oracle
+    st, r = oracle_and_gpu(M, 532, 256, groups=[(500, 532)], seed=8, scale=3.0)
+    zz = torch.rand(300, 500, generator=torch.Generator().manual_seed(2))
+    close(E.class_free_energies(r, zz.to(DEV), 32, 500), O.class_free_energies(st, zz, 32, 500),
+          dict(rtol=2e-5, atol=2e-3))
+    from multimodal_idbn_b200.energy_utils import _label_trajectory
+    traj = _label_trajectory(r, zz.to(DEV), 500, 32, 5)
+    v = torch.cat([zz, torch.full((300, 32), 1.0 / 32)], 1)
+    for t in range(5):
+        v = O.img2txt_lite_step(st, v, 500, 32)
+        close(traj[t], v[:, 500:], dict(rtol=1e-4, atol=2e-6))
+    assert torch.allclose(traj.sum(-1).cpu(), torch.ones(5, 300), atol=1e-5)
+
+
 # ------------------------------------------------------------------------------ oracle at size
 def oracle_and_gpu(M, V, H, groups=None, seed=0, scale=1.0, **hyper):
     st = O.new_state(V, H, seed=seed, groups=groups, **hyper)

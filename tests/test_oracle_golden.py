@@ -272,3 +272,29 @@ def test_bimodal_bias_init_cross_reconstruct_and_train_joint():
     np.testing.assert_allclose([h["mod1_mse"] for h in hist], g["mod1_mse"], rtol=1e-5)
     np.testing.assert_allclose([h["mod2_mse"] for h in hist], g["mod2_mse"], rtol=1e-5)
     np.testing.assert_allclose([h["cd_loss"] for h in hist if h["cd_loss"] == h["cd_loss"]], g["cd_loss"], rtol=1e-5)
+
+
+TRACE_LISTS = ("p_top1", "p_top2", "p_gap", "p_gt", "deltaF_pred_traj")
+TRACE_SCALARS = ("steps_to_converge", "kstar", "predT", "margin_energy", "fe_top1_final", "fe_gap_final", "gt")
+
+
+def test_energy_diagnostics():
+    """utils/energy_utils.py: class_free_energies and trace_single_img2txt against the reference's own run."""
+    g = load_golden("energy")
+    K = int(g["K"])
+    layers = [state_from(g, f"l{i}_") for i in range(2)]
+    joint = state_from(g, "joint_", [(12, 12 + K)])
+    x = T(g["x"]).reshape(g["x"].shape[0], -1)
+    z = O.idbn_represent(layers, x)
+    torch.testing.assert_close(O.class_free_energies(joint, z, K, 12), T(g["Fk"]), rtol=1e-5, atol=1e-5)
+    # F_k is the free energy of [z, e_k]
+    ek = torch.eye(K)
+    brute = torch.stack([O.free_energy(joint, torch.cat([z, ek[k].expand(z.shape[0], K)], 1)) for k in range(K)], 1)
+    torch.testing.assert_close(O.class_free_energies(joint, z, K, 12), brute, rtol=1e-5, atol=1e-5)
+    for i in range(4):
+        tr = O.trace_single_img2txt(layers, joint, x[i:i + 1], int(g[f"t{i}_gt"]), K, steps=12, eps_l1=1e-4,
+                                    stable_steps=3, gap_thresh=0.9)
+        for key in TRACE_LISTS:
+            np.testing.assert_allclose(tr[key], g[f"t{i}_{key}"], rtol=1e-5, atol=1e-6, err_msg=key)
+        for key in TRACE_SCALARS:
+            np.testing.assert_allclose(tr[key], g[f"t{i}_{key}"], rtol=1e-5, atol=1e-6, err_msg=key)
