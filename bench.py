@@ -280,6 +280,7 @@ def run_ours(args):
     # ---------------- second metric of BASELINE.json: cross-modal chain-steps/s (config C4 shapes,
     # this rank's share of the 65 536 chains: joint RBM (500+32)->256, 50 steps, both directions)
     chains = chain_steps_metric(M, dev, 65536 // max(1, world) if world > 1 else 8192)
+    large = large_batch_metric(M, dev) if rank == 0 and world == 1 else None
 
     if rank != 0:
         return
@@ -308,7 +309,7 @@ def run_ours(args):
                             (v["ms_avg"] * 1e-3) / 1e9 if v["ms_avg"] else None) for k, v in kern.items()},
         "roofline_step": {"algorithmic_bytes": sb, "achieved_gbs": step_gbs, "frac": step_gbs / peak},
         "cpu_baseline": cpu,
-        "extra": {"chain_steps_per_s": chains},
+        "extra": {"chain_steps_per_s": chains, "large_batch": large},
     }
     print(json.dumps(line), flush=True)
 
@@ -338,6 +339,34 @@ def chain_steps_metric(M, dev, n_chains, steps=50):
         out[name] = n_chains * steps * 3 / (e0.elapsed_time(e1) * 1e-3)
     r._mu_pull = None
     return out
+
+
+def large_batch_metric(M, dev, B=8192, V=10000, H=4096, steps=4):
+    """Tensor-bound end of the sweep (BASELINE config C5, widened layer 10000 -> 4096): CD-1 updates at batch
+    `B` in tf32 mode; FLOPs = (3 + 2k) * 2 * B * V * H; the roofline is the TF32 dense peak = half the
+    measured bf16 figure of MEASURED_PEAKS.json (sustained: the kernels run back to back for ~0.2 s)."""
+    r = M.RBM(V, H, 0.1, 1e-4, 0.5).to(dev)
+    x = (torch.rand(B, V, device=dev) < 0.1).float()
+    for _ in range(2):
+        r.train_epoch(x, 0, 1, CD=1)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        r.train_epoch(x, 0, 1, CD=1)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    tflops = 5 * 2.0 * B * V * H / (ms * 1e-3) / 1e12
+    peak = None
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+            peak = float(json.load(f)["bf16_tflops_sustained"]) / 2
+    except Exception:                                   # noqa: BLE001
+        pass
+    del r, x
+    torch.cuda.empty_cache()
+    return {"workload": f"RBM {V}->{H} CD-1 batch {B}, tf32", "ms_per_step": ms, "samples_per_s": B / (ms * 1e-3),
+            "tflops": tflops, "tf32_peak_tflops": peak, "frac": tflops / peak if peak else None}
 
 
 def main():
