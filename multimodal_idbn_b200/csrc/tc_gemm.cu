@@ -406,10 +406,14 @@ int tc_gemm_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* vp, const flo
     if (!aligned16(vp) || !aligned16(hp) || !aligned16(vn) || !aligned16(hn) || (dS_out && !aligned16(dS_out)) ||
         (!dS_out && !aligned16(r->Wm)))
         return fail(ctx, -1, "tc stats: pointers must be 16-byte aligned");
+    // tile shape: HBM-bound small batches stream W / W_m through 128 x 128 tiles and four IO slots; from 512 rows
+    // the kernel is tensor-bound and uses 128 x 256 tiles (more MACs per operand byte), three operand stages
+    const bool wide = B >= 512 && r->H >= 256 && getenv("IMDBN_STATS_NARROW") == nullptr;
+    const int BN = wide ? 256 : 128;
     StatsArgs a{};
     a.V = r->V; a.H = r->H; a.B = B;
     a.m_tiles = (r->V + ST_BM - 1) / ST_BM;
-    a.n_tiles = (r->H + ST_BN - 1) / ST_BN;
+    a.n_tiles = (r->H + BN - 1) / BN;
     a.k_chunks = (B + ST_KC - 1) / ST_KC;
     if (upd) { a.lr = upd->lr; a.mom = upd->momentum; a.wd = upd->weight_decay; a.bsz = (float)upd->batch_global; }
     { static const int dbg_env = getenv("IMDBN_DEBUG_STATS") ? atoi(getenv("IMDBN_DEBUG_STATS")) : 0; a.dbg = dbg_env; }
@@ -425,15 +429,23 @@ int tc_gemm_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* vp, const flo
     const CUtensorMap* tWm = dS_out ? tW : get_map(ctx, r->Wm, r->H, r->V, ST_BM, false);
     if (!tVP || !tVN || !tHP || !tHN || !tW || !tWm) return fail(ctx, -5, "cuTensorMapEncodeTiled failed");
     const int G = std::min(ctx->num_sms, a.m_tiles * a.n_tiles);
-    if (dS_out) {
-        static bool set0 = false;
-        if (!set0) { IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_tc_stats<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM)); set0 = true; }
-        IMDBN_CUDA(ctx, launch_pdl(k_tc_stats<false>, dim3(G), dim3(ST_THREADS), ST_SMEM, st, *tVP, *tVN, *tHP, *tHN, *tW, *tWm, a));
-    } else {
-        static bool set1 = false;
-        if (!set1) { IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_tc_stats<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM)); set1 = true; }
-        IMDBN_CUDA(ctx, launch_pdl(k_tc_stats<true>, dim3(G), dim3(ST_THREADS), ST_SMEM, st, *tVP, *tVN, *tHP, *tHN, *tW, *tWm, a));
-    }
+    auto launch = [&](auto kernel, int smem, bool& attr_set) -> cudaError_t {
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return e;
+            attr_set = true;
+        }
+        return launch_pdl(kernel, dim3(G), dim3(ST_THREADS), (size_t)smem, st, *tVP, *tVN, *tHP, *tHN, *tW, *tWm, a);
+    };
+    static bool set[4] = {false, false, false, false};
+    cudaError_t e;
+    if (wide)
+        e = dS_out ? launch(k_tc_stats<false, 256, 3, 2>, st_smem<256, 3, 2>(), set[0])
+                   : launch(k_tc_stats<true, 256, 3, 2>, st_smem<256, 3, 2>(), set[1]);
+    else
+        e = dS_out ? launch(k_tc_stats<false, 128, 2, 4>, st_smem<128, 2, 4>(), set[2])
+                   : launch(k_tc_stats<true, 128, 2, 4>, st_smem<128, 2, 4>(), set[3]);
+    IMDBN_CUDA(ctx, e);
     IMDBN_CHECK_LAUNCH(ctx, "k_tc_stats");
     return 0;
 }

@@ -18,19 +18,22 @@
 #pragma once
 
 constexpr int ST_BM = 128;                 // visible units per tile (MMA M)
-constexpr int ST_BN = 128;                 // hidden units per tile  (MMA N)
 constexpr int ST_KC = 16;                  // batch rows per operand stage
-constexpr int ST_STAGES = 2;
 constexpr int ST_THREADS = 384;            // 12 warps, roles above
 constexpr int ST_EPI_WARPS = 8;
 constexpr int ST_OP_BOX = ST_KC * 128;                 // one [16 x 32 floats] box = 2 KB
 constexpr int ST_SEG_A = (ST_BM / 32) * ST_OP_BOX;     // 8 KB
-constexpr int ST_SEG_B = (ST_BN / 32) * ST_OP_BOX;     // 8 KB
-constexpr int ST_STAGE_BYTES = 2 * (ST_SEG_A + ST_SEG_B);   // positive + negative phase: 32 KB
 constexpr int ST_IO_BOX = ST_BM * 128;                 // [128 rows x 32 floats] = 16 KB
-constexpr int ST_NSLOT = 4;                            // IO slots (power of two)
-constexpr int ST_SLOT_BYTES = 2 * ST_IO_BOX;           // W + W_m quarter-tile [128 x 32] each: 32 KB
-constexpr int ST_SMEM = ST_STAGES * ST_STAGE_BYTES + ST_NSLOT * ST_SLOT_BYTES + 1024 /*barriers*/ + 1024 /*align*/;
+constexpr int ST_SLOT_BYTES = 2 * ST_IO_BOX;           // W + W_m column slice [128 x 32] each: 32 KB
+// Two shapes of the same kernel:
+//   small batch (HBM-bound, the update streams W / W_m): 128 x 128 tiles, 2 operand stages, 4 IO slots;
+//   large batch (tensor-bound, B >= 512): 128 x 256 tiles (21 MACs per operand byte instead of 16), 3 operand
+//   stages, 2 IO slots -- the weight traffic is negligible there.
+template <int BN> __host__ __device__ constexpr int st_seg_b() { return (BN / 32) * ST_OP_BOX; }
+template <int BN> __host__ __device__ constexpr int st_stage_bytes() { return 2 * (ST_SEG_A + st_seg_b<BN>()); }   // positive + negative phase
+template <int BN, int STAGES, int NSLOT> __host__ __device__ constexpr int st_smem() {
+    return STAGES * st_stage_bytes<BN>() + NSLOT * ST_SLOT_BYTES + 1024 /*barriers*/ + 1024 /*align*/;
+}
 
 struct StatsArgs {
     int V, H, B;
@@ -41,24 +44,28 @@ struct StatsArgs {
     int dbg;    // experiment switch (IMDBN_DEBUG_STATS): 1 = no operands/MMA, 2 = no W/W_m traffic
 };
 
-template <bool UPDATE>
+template <bool UPDATE, int ST_BN, int ST_STAGES, int ST_NSLOT>
 __global__ void __launch_bounds__(ST_THREADS, 1)
 k_tc_stats(const __grid_constant__ CUtensorMap tmVP, const __grid_constant__ CUtensorMap tmVN,
            const __grid_constant__ CUtensorMap tmHP, const __grid_constant__ CUtensorMap tmHN,
            const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWm, StatsArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int ST_SEG_B = st_seg_b<ST_BN>();
+    constexpr int ST_STAGE_BYTES = st_stage_bytes<ST_BN>();
+    constexpr int ST_SLICES = ST_BN / 32;                      // 32-column slices of W / W_m per tile
+    static_assert(ST_STAGES <= 4 && ST_NSLOT <= 4 && (ST_NSLOT & (ST_NSLOT - 1)) == 0, "ring sizes");
     uint8_t* ops = smem;                                       // operand ring
-    uint8_t* slots = smem + ST_STAGES * ST_STAGE_BYTES;        // 2 IO slots
+    uint8_t* slots = smem + ST_STAGES * ST_STAGE_BYTES;        // IO slots
     uint64_t* bars = reinterpret_cast<uint64_t*>(slots + ST_NSLOT * ST_SLOT_BYTES);
-    uint64_t* ops_full = bars;            // [2]
-    uint64_t* ops_empty = bars + 2;       // [2]
-    uint64_t* acc_full = bars + 4;        // [2]
-    uint64_t* acc_empty = bars + 6;       // [2]
-    uint64_t* io_full = bars + 8;         // [ST_NSLOT]
-    uint64_t* io_written = bars + 12;     // [ST_NSLOT]
-    uint64_t* io_empty = bars + 16;       // [ST_NSLOT]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+    uint64_t* ops_full = bars;            // [ST_STAGES <= 4]
+    uint64_t* ops_empty = bars + 4;       // [ST_STAGES]
+    uint64_t* acc_full = bars + 8;        // [2]
+    uint64_t* acc_empty = bars + 10;      // [2]
+    uint64_t* io_full = bars + 12;        // [ST_NSLOT <= 4]
+    uint64_t* io_written = bars + 16;     // [ST_NSLOT]
+    uint64_t* io_empty = bars + 20;       // [ST_NSLOT]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles_total = a.m_tiles * a.n_tiles;
@@ -71,10 +78,8 @@ k_tc_stats(const __grid_constant__ CUtensorMap tmVP, const __grid_constant__ CUt
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmVP); tma_prefetch_desc(&tmVN); tma_prefetch_desc(&tmHP); tma_prefetch_desc(&tmHN);
         tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmWm);
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&ops_full[s], 1); mbar_init(&ops_empty[s], 1);
-            mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], ST_EPI_WARPS);
-        }
+        for (int s = 0; s < ST_STAGES; ++s) { mbar_init(&ops_full[s], 1); mbar_init(&ops_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], ST_EPI_WARPS); }
         for (int s = 0; s < ST_NSLOT; ++s) {
             mbar_init(&io_full[s], 1); mbar_init(&io_written[s], ST_EPI_WARPS / 2); mbar_init(&io_empty[s], 1);
         }
@@ -154,7 +159,7 @@ k_tc_stats(const __grid_constant__ CUtensorMap tmVP, const __grid_constant__ CUt
             int hh = 0;
             for (int t = t_beg; t < t_end; t += t_step) {
                 const int m0 = (t / a.n_tiles) * ST_BM, n0 = (t % a.n_tiles) * ST_BN;
-                for (int qt = 0; qt < 4; ++qt, ++hh) {
+                for (int qt = 0; qt < ST_SLICES; ++qt, ++hh) {
                     const int s = hh & (ST_NSLOT - 1);
                     uint8_t* slot = slots + s * ST_SLOT_BYTES;
                     mbar_wait(&io_empty[s], ((hh / ST_NSLOT) & 1) ^ 1);
@@ -170,7 +175,7 @@ k_tc_stats(const __grid_constant__ CUtensorMap tmVP, const __grid_constant__ CUt
             int hh = 0;
             for (int t = t_beg; t < t_end; t += t_step) {
                 const int m0 = (t / a.n_tiles) * ST_BM, n0 = (t % a.n_tiles) * ST_BN;
-                for (int qt = 0; qt < 4; ++qt, ++hh) {
+                for (int qt = 0; qt < ST_SLICES; ++qt, ++hh) {
                     const int s = hh & (ST_NSLOT - 1);
                     const uint8_t* slot = slots + s * ST_SLOT_BYTES;
                     mbar_wait(&io_written[s], (hh / ST_NSLOT) & 1);
@@ -206,9 +211,9 @@ k_tc_stats(const __grid_constant__ CUtensorMap tmVP, const __grid_constant__ CUt
             if (a.dbg != 1) mbar_wait(&acc_full[buf], (seg >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int qi = 0; qi < 2; ++qi) {
+            for (int qi = 0; qi < ST_SLICES / 2; ++qi) {
                 const int qt = grp + 2 * qi;
-                const int hh = seg * 4 + qt;
+                const int hh = seg * ST_SLICES + qt;
                 const int s = hh & (ST_NSLOT - 1);
                 uint8_t* wrow = slots + s * ST_SLOT_BYTES + row * 128;
                 uint8_t* mrow = wrow + ST_IO_BOX;
@@ -221,7 +226,7 @@ k_tc_stats(const __grid_constant__ CUtensorMap tmVP, const __grid_constant__ CUt
 #pragma unroll
                     for (int i = 0; i < 16; ++i) { acc[i] = v0[i]; acc[16 + i] = v1[i]; }
                 }
-                if (qi == 1) {                         // this warp has read its share of the accumulator
+                if (qi == ST_SLICES / 2 - 1) {         // this warp has read its share of the accumulator
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&acc_empty[buf]);
