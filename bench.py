@@ -183,6 +183,9 @@ def run_ours(args):
     torch.manual_seed(0)
     os.chdir(os.environ.get("TMPDIR", "/tmp"))       # iDBN creates logs-idbn/ in CWD (idbn.py:115)
     model = M.iDBN(LAYERS, dict(PARAMS), None, None, dev)
+    if args.pipeline_reserve >= 0 and world == 1:
+        model.pipeline_layers = True
+        model.pipeline_reserve_sms = args.pipeline_reserve
     g = torch.Generator().manual_seed(1234)
     host = (torch.rand(N_DISTINCT_BATCHES, BATCH, LAYERS[0], generator=g) < 0.10).float().pin_memory()
     resident = host.to(dev)
@@ -223,6 +226,7 @@ def run_ours(args):
     for i in range(steps):
         # the loop knows its next minibatch (as iDBN.train does through the prefetcher)
         model.train_step(batch(warm + i), 0, 1, next_v=batch(warm + i + 1))
+    model.sync()                                                   # (pipelined layers: join the side stream)
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
@@ -377,6 +381,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pipeline-reserve", type=int, default=-1,
+                    help="SMs left to the upper layers, which then run on a side stream concurrently with the next "
+                         "layer-0 update (-1 = layers run back to back on one stream)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

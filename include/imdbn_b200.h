@@ -78,6 +78,11 @@ int imdbn_ctx_create(imdbn_ctx** out, int device);
 void imdbn_ctx_destroy(imdbn_ctx* ctx);
 const char* imdbn_last_error(imdbn_ctx* ctx);
 int imdbn_set_precision(imdbn_ctx* ctx, int prec);
+/* Upper bound on the SMs the persistent tensor-core kernels launched through this context occupy (0 = all).
+ * A context is bound to one stream: limiting the context that trains the large bottom layer leaves SMs to the
+ * context (stream) that trains the small upper layers of an iDBN at the same time (idbn.py:199-204 pipelined
+ * over minibatches: layer 0 of batch t+1 does not depend on the upper layers of batch t). */
+int imdbn_set_sm_limit(imdbn_ctx* ctx, int n_sms);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t imdbn_launch_count(imdbn_ctx* ctx);
 

@@ -91,6 +91,7 @@ SIGNATURES = {
     "imdbn_cd_stats": (_I, [_P, C.POINTER(RbmStruct), _P, _I, _I, C.POINTER(RngStruct), _P, _P, _P]),
     "imdbn_stats_size": (C.c_int64, [C.POINTER(RbmStruct)]),
     "imdbn_apply_update": (_I, [_P, C.POINTER(RbmStruct), _P, C.POINTER(UpdateStruct), _P, _P]),
+    "imdbn_set_sm_limit": (_I, [_P, _I]),
     "imdbn_dp_update": (_I, [_P, C.POINTER(RbmStruct), C.POINTER(PeersStruct), C.POINTER(UpdateStruct), _P, _P]),
     "imdbn_class_free_energies": (_I, [_P, C.POINTER(RbmStruct), _P, _I, _I, _P, _P]),
     "imdbn_trace_img2txt": (_I, [_P, C.POINTER(RbmStruct), _P, _I, _I, _P, _I, _P, _P]),
@@ -160,6 +161,10 @@ class Context:
         if prec != self.precision:
             self.check(self.lib.imdbn_set_precision(self.handle, int(prec)), "imdbn_set_precision")
             self.precision = prec
+
+    def set_sm_limit(self, n_sms: int):
+        """At most ``n_sms`` SMs for the persistent tensor-core kernels of this context (0 = all)."""
+        self.check(self.lib.imdbn_set_sm_limit(self.handle, int(n_sms)), "imdbn_set_sm_limit")
 
     def profile(self, enable: bool):
         self.check(self.lib.imdbn_profile_enable(self.handle, int(enable)), "imdbn_profile_enable")

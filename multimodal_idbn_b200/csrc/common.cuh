@@ -31,6 +31,7 @@ struct imdbn_ctx {
     std::vector<imdbn::ProfRec> prof;
     int device = 0;
     int num_sms = imdbn::kNumSMsFallback;
+    int tc_sms = 0;                   // > 0: persistent tensor-core kernels of this context use at most this many SMs
     int precision = IMDBN_PREC_FP32;
     int64_t launches = 0;
     std::string err;
@@ -43,6 +44,12 @@ struct imdbn_ctx {
 };
 
 namespace imdbn {
+
+// SMs the persistent tensor-core kernels may occupy (imdbn_set_sm_limit): leaves the rest of the chip to kernels
+// of another stream, e.g. the upper layers of an iDBN running concurrently with the next layer-0 update.
+inline int tc_sms(const imdbn_ctx* ctx) {
+    return ctx->tc_sms > 0 && ctx->tc_sms < ctx->num_sms ? ctx->tc_sms : ctx->num_sms;
+}
 
 inline int fail(imdbn_ctx* ctx, int code, const char* what) {
     if (ctx) {

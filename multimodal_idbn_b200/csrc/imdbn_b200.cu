@@ -766,6 +766,12 @@ void imdbn_ctx_destroy(imdbn_ctx* ctx) {
 
 const char* imdbn_last_error(imdbn_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
+int imdbn_set_sm_limit(imdbn_ctx* ctx, int n_sms) {
+    IMDBN_ARG(ctx, ctx && n_sms >= 0);
+    ctx->tc_sms = n_sms;
+    return 0;
+}
+
 int imdbn_set_precision(imdbn_ctx* ctx, int prec) {
     IMDBN_ARG(ctx, ctx && (prec == IMDBN_PREC_FP32 || prec == IMDBN_PREC_TF32));
     ctx->precision = prec;

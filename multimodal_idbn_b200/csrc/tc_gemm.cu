@@ -301,7 +301,7 @@ SKPlan tc_plan(const imdbn_ctx* ctx, int M_total, int K_total) {
     p.k_iters = (K_total + TS_BK - 1) / TS_BK;
     const int total = m_tiles * p.k_iters;
     // at least 4 k-iterations per CTA: fewer, longer ranges for small layers (fewer slabs to add)
-    const int G = std::max(1, std::min(ctx->num_sms, total / 4));
+    const int G = std::max(1, std::min(tc_sms(ctx), total / 4));
     p.q = total / G;
     p.r = total % G;
     p.tile_w = TS_BM;
@@ -428,7 +428,7 @@ int tc_gemm_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* vp, const flo
     const CUtensorMap* tW = get_map(ctx, dS_out ? dS_out : r->W, r->H, r->V, ST_BM, false);
     const CUtensorMap* tWm = dS_out ? tW : get_map(ctx, r->Wm, r->H, r->V, ST_BM, false);
     if (!tVP || !tVN || !tHP || !tHN || !tW || !tWm) return fail(ctx, -5, "cuTensorMapEncodeTiled failed");
-    const int G = std::min(ctx->num_sms, a.m_tiles * a.n_tiles);
+    const int G = std::min(tc_sms(ctx), a.m_tiles * a.n_tiles);
     auto launch = [&](auto kernel, int smem, bool& attr_set) -> cudaError_t {
         if (!attr_set) {
             cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

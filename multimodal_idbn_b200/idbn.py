@@ -17,6 +17,7 @@ from typing import Iterable, List, Optional
 
 import torch
 
+from . import _lib as L
 from .rbm import RBM
 
 
@@ -157,8 +158,6 @@ class iDBN:
         optional fp32 vector with one element per layer (device or PINNED host memory) that the kernels
         write the losses into directly; the returned list then holds views of it."""
         v = _flat(v, self.device)
-        if loss_out is not None and getattr(self, "pipeline_layers", False):
-            raise ValueError("loss_out is not supported together with pipeline_layers")
         if len(self.layers) == 1 or not getattr(self, "pipeline_layers", False) or v.device.type != "cuda":
             losses = []
             for i, rbm in enumerate(self.layers):
@@ -167,16 +166,28 @@ class iDBN:
                                               loss_out=None if loss_out is None else loss_out[i])
                 losses.append(loss)
             return losses
-        # Optional (pipeline_layers = True; measured slower on B200 because the 197 KB tensor-core CTAs of the
-        # two layers cannot share an SM, so it is off by default):
-        # Layer 0 of minibatch t+1 does not depend on the upper layers of minibatch t (they only consume
-        # layer 0's forward output), so the upper layers run on a side stream and overlap the next
-        # layer-0 update.  Results are identical; `sync()` (or `loss_ready`) orders readers of the losses.
+        # pipeline_layers = True (off by default: measured 215 us against 175 us per C2 step on B200 -- the step is
+        # then bound by the HOST, whose enqueue cost rises from ~125 to ~210 us with the extra events and stream
+        # switches, although the GPU work does overlap): layer 0 of minibatch t+1 does not depend on the upper layers of minibatch t
+        # (they only consume layer 0's forward output), so the upper layers run on a side stream and overlap
+        # the next layer-0 update.  The persistent tensor-core kernels of layer 0 are confined to
+        # num_sms - pipeline_reserve_sms SMs (their 197 KB CTAs would otherwise own every SM and the small
+        # upper-layer kernels would queue behind them); the upper layers' kernels run on the SMs left over.
+        # Results are identical; `sync()` (or `loss_ready`) orders readers of the losses and of the upper
+        # layers' parameters.
         main = torch.cuda.current_stream(v.device)
         side = self.__dict__.get("_side_stream")
         if side is None:
             side = self._side_stream = torch.cuda.Stream(device=v.device)
-        loss0, h = self.layers[0].train_epoch_fwd(v, epoch, epochs, CD=self.cd_k, next_data=next_v)
+        reserve = int(getattr(self, "pipeline_reserve_sms", 16))
+        ctx0, _ = L.context_for(v)
+        if self.__dict__.get("_sm_limit_set") != (id(ctx0), reserve):
+            n_sms = torch.cuda.get_device_properties(v.device).multi_processor_count
+            ctx0.set_sm_limit(max(8, n_sms - reserve) if reserve > 0 else 0)
+            self._sm_limit_set = (id(ctx0), reserve)
+        prev = self.__dict__.get("loss_ready")
+        loss0, h = self.layers[0].train_epoch_fwd(v, epoch, epochs, CD=self.cd_k, next_data=next_v,
+                                                  loss_out=None if loss_out is None else loss_out[0])
         ready = torch.cuda.Event()
         ready.record(main)
         h.record_stream(side)
@@ -184,13 +195,16 @@ class iDBN:
         with torch.cuda.stream(side):
             side.wait_event(ready)
             x = h
-            for rbm in self.layers[1:]:
-                loss, x = rbm.train_epoch_fwd(x, epoch, epochs, CD=self.cd_k)
-                loss.record_stream(main)
+            for i, rbm in enumerate(self.layers[1:], start=1):
+                loss, x = rbm.train_epoch_fwd(x, epoch, epochs, CD=self.cd_k,
+                                              loss_out=None if loss_out is None else loss_out[i])
+                if loss_out is None:
+                    loss.record_stream(main)
                 losses.append(loss)
             done = torch.cuda.Event()
             done.record(side)
         self.loss_ready = done
+        del prev
         return losses
 
     def sync(self) -> None:
