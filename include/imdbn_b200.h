@@ -139,6 +139,18 @@ int imdbn_cd_train_fwd(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* data, 
                        const float* pos_h_in, const float* next_data, int B_next, float* fwd_out,
                        imdbn_stream stream);
 
+/* One minibatch of iDBN.train for all layers (idbn.py:199-204): layer l trains on fwd_out[l-1] rows [0,B) (layer 0
+ * on `data`, with pos_h_in / next_data / B_next as in imdbn_cd_train_fwd) and writes forward(input) under its
+ * updated parameters to fwd_out[l] ([B (+B_next for l = 0), H_l]); loss_out[l] = one float (device or mapped pinned
+ * host memory).  ctx1 / stream1 non-NULL: layers >= 1 are enqueued on stream1 behind an event, so they overlap
+ * whatever follows on stream0 -- the next minibatch's layer 0, which does not depend on them; the caller must then
+ * alternate between TWO sets of fwd_out buffers (the call waits for the readers of the set used two calls ago). */
+int imdbn_idbn_train_step(imdbn_ctx* ctx0, imdbn_ctx* ctx1, int n_layers, const imdbn_rbm* rbms,
+                          const imdbn_update* upds, const imdbn_rng* rngs, const float* data, int B, int k,
+                          const float* pos_h_in, const float* next_data, int B_next, float* const* fwd_out,
+                          float* const* loss_out, int buffer_set /* 0 | 1: which set fwd_out belongs to */,
+                          imdbn_stream stream0, imdbn_stream stream1);
+
 /* The same statistics without the update, for batches sharded over ranks: writes the local sums
  *   stats_out = [ dS (V*H) | dh (H) | dv (V) | pos_h column sum (H) | squared error (1) ]
  * which the host all-reduces (NCCL) and hands to imdbn_apply_update on every rank. */

@@ -92,6 +92,8 @@ SIGNATURES = {
     "imdbn_stats_size": (C.c_int64, [C.POINTER(RbmStruct)]),
     "imdbn_apply_update": (_I, [_P, C.POINTER(RbmStruct), _P, C.POINTER(UpdateStruct), _P, _P]),
     "imdbn_set_sm_limit": (_I, [_P, _I]),
+    "imdbn_idbn_train_step": (_I, [_P, _P, _I, C.POINTER(RbmStruct), C.POINTER(UpdateStruct), C.POINTER(RngStruct), _P, _I,
+                                   _I, _P, _P, _I, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _I, _P, _P]),
     "imdbn_dp_update": (_I, [_P, C.POINTER(RbmStruct), C.POINTER(PeersStruct), C.POINTER(UpdateStruct), _P, _P]),
     "imdbn_class_free_energies": (_I, [_P, C.POINTER(RbmStruct), _P, _I, _I, _P, _P]),
     "imdbn_trace_img2txt": (_I, [_P, C.POINTER(RbmStruct), _P, _I, _I, _P, _I, _P, _P]),

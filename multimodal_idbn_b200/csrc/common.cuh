@@ -41,6 +41,9 @@ struct imdbn_ctx {
     void* tc = nullptr;  // tensor-core path state (tc_gemm.cu), opaque here
     bool stats_after_colstats = false;   // next tc statistics kernel directly follows k_colstats (see tc_stats.cuh)
     unsigned int* ticket = nullptr;   // device counter of the last-block reductions (self-resetting)
+    // imdbn_idbn_train_step with a second context: cross-stream events (created lazily)
+    cudaEvent_t ev_ready = nullptr;
+    cudaEvent_t ev_done[2] = {nullptr, nullptr};
 };
 
 namespace imdbn {
@@ -105,6 +108,11 @@ struct ProfScope {
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Early launch of dependents can be switched off for a span of launches (pdl_early() = false): a dependent grid
+// that is launched early parks its CTAs on whatever SMs are free, which defeats leaving SMs to another stream
+// (imdbn_idbn_train_step with pipelined layers).
+inline bool& pdl_early() { static thread_local bool on = true; return on; }
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                               Args&&... args) {
@@ -113,7 +121,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_early() ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

@@ -760,6 +760,9 @@ void imdbn_ctx_destroy(imdbn_ctx* ctx) {
     tc_destroy(ctx);
     prof_clear(ctx);
     if (ctx->ticket) cudaFree(ctx->ticket);
+    if (ctx->ev_ready) cudaEventDestroy(ctx->ev_ready);
+    for (int i = 0; i < 2; ++i)
+        if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
     if (ctx->arena.base) cudaFree(ctx->arena.base);
     delete ctx;
 }
@@ -890,6 +893,56 @@ int imdbn_cd_train_fwd(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* data, 
     IMDBN_ARG(ctx, upd && upd->batch_global > 0 && fwd_out && (!next_data || B_next > 0));
     FwdTail t{pos_h_in, next_data, next_data ? B_next : 0, fwd_out};
     return cd_core(ctx, rbm, data, B, k, upd, rng, loss_out, nullptr, (cudaStream_t)stream, &t);
+}
+
+// One minibatch of iDBN.train for ALL layers in one call (idbn.py:199-204): per layer CD-k update + forward of
+// the updated layer, which is the next layer's input.  With a second context / stream the upper layers run
+// there, concurrently with whatever the caller enqueues next on the first stream (the next minibatch's layer 0).
+int imdbn_idbn_train_step(imdbn_ctx* ctx0, imdbn_ctx* ctx1, int n_layers, const imdbn_rbm* rbms,
+                          const imdbn_update* upds, const imdbn_rng* rngs, const float* data, int B, int k,
+                          const float* pos_h_in, const float* next_data, int B_next, float* const* fwd_out,
+                          float* const* loss_out, int buffer_set, imdbn_stream stream0, imdbn_stream stream1) {
+    IMDBN_ARG(ctx0, ctx0 && n_layers >= 1 && rbms && upds && rngs && data && fwd_out && loss_out && B > 0);
+    IMDBN_ARG(ctx0, buffer_set == 0 || buffer_set == 1);
+    cudaStream_t s0 = (cudaStream_t)stream0, s1 = (cudaStream_t)stream1;
+    const bool piped = ctx1 != nullptr && n_layers > 1;
+    const int par = buffer_set;
+    if (piped) {
+        if (!ctx0->ev_ready) {
+            IMDBN_CUDA(ctx0, cudaEventCreateWithFlags(&ctx0->ev_ready, cudaEventDisableTiming));
+            for (int i = 0; i < 2; ++i)
+                IMDBN_CUDA(ctx0, cudaEventCreateWithFlags(&ctx0->ev_done[i], cudaEventDisableTiming));
+        } else {
+            // the caller alternates between two sets of fwd_out buffers: wait for the upper layers that last read
+            // the set written now (an event that was never recorded is complete)
+            IMDBN_CUDA(ctx0, cudaStreamWaitEvent(s0, ctx0->ev_done[par], 0));
+        }
+    }
+    for (int l = 0; l < n_layers; ++l) IMDBN_ARG(ctx0, fwd_out[l] && upds[l].batch_global > 0);
+    FwdTail t0{pos_h_in, next_data, next_data ? B_next : 0, fwd_out[0]};
+    static const bool keep_pdl = getenv("IMDBN_PIPE_PDL") != nullptr;
+    if (piped && !keep_pdl) pdl_early() = false;
+    int rc = cd_core(ctx0, &rbms[0], data, B, k, &upds[0], &rngs[0], loss_out[0], nullptr, s0, &t0);
+    pdl_early() = true;
+    if (rc) return rc;
+    imdbn_ctx* cx = ctx0;
+    cudaStream_t sx = s0;
+    if (piped) {
+        IMDBN_CUDA(ctx0, cudaEventRecord(ctx0->ev_ready, s0));
+        IMDBN_CUDA(ctx0, cudaStreamWaitEvent(s1, ctx0->ev_ready, 0));
+        cx = ctx1; sx = s1;
+        cx->precision = ctx0->precision;
+    }
+    for (int l = 1; l < n_layers; ++l) {
+        FwdTail t{nullptr, nullptr, 0, fwd_out[l]};
+        rc = cd_core(cx, &rbms[l], fwd_out[l - 1], B, k, &upds[l], &rngs[l], loss_out[l], nullptr, sx, &t);
+        if (rc) {
+            if (cx != ctx0) ctx0->err = cx->err;
+            return rc;
+        }
+    }
+    if (piped) IMDBN_CUDA(ctx0, cudaEventRecord(ctx0->ev_done[par], s1));
+    return 0;
 }
 
 int64_t imdbn_stats_size(const imdbn_rbm* r) {

@@ -11,6 +11,7 @@ logged when a ``wandb_run`` is given.
 """
 from __future__ import annotations
 
+import ctypes as C
 import os
 import pickle
 from typing import Iterable, List, Optional
@@ -18,6 +19,7 @@ from typing import Iterable, List, Optional
 import torch
 
 from . import _lib as L
+from . import dist as _dist
 from .rbm import RBM
 
 
@@ -158,78 +160,122 @@ class iDBN:
         optional fp32 vector with one element per layer (device or PINNED host memory) that the kernels
         write the losses into directly; the returned list then holds views of it."""
         v = _flat(v, self.device)
-        if len(self.layers) == 1 or not getattr(self, "pipeline_layers", False) or v.device.type != "cuda":
-            losses = []
-            for i, rbm in enumerate(self.layers):
-                loss, v = rbm.train_epoch_fwd(v, epoch, epochs, CD=self.cd_k,
-                                              next_data=next_v if i == 0 else None,
-                                              loss_out=None if loss_out is None else loss_out[i])
-                losses.append(loss)
-            return losses
-        # pipeline_layers = True (off by default: measured 215 us against 175 us per C2 step on B200 -- the step is
-        # then bound by the HOST, whose enqueue cost rises from ~125 to ~210 us with the extra events and stream
-        # switches, although the GPU work does overlap): layer 0 of minibatch t+1 does not depend on the upper layers of minibatch t
-        # (they only consume layer 0's forward output), so the upper layers run on a side stream and overlap
-        # the next layer-0 update.  The persistent tensor-core kernels of layer 0 are confined to
-        # num_sms - pipeline_reserve_sms SMs (their 197 KB CTAs would otherwise own every SM and the small
-        # upper-layer kernels would queue behind them); the upper layers' kernels run on the SMs left over.
-        # Results are identical; `sync()` (or `loss_ready`) orders readers of the losses and of the upper
-        # layers' parameters.
-        main = torch.cuda.current_stream(v.device)
-        side = self.__dict__.get("_side_stream")
-        if side is None:
-            side = self._side_stream = torch.cuda.Stream(device=v.device)
-        reserve = int(getattr(self, "pipeline_reserve_sms", 16))
-        ctx0, _ = L.context_for(v)
-        if self.__dict__.get("_sm_limit_set") != (id(ctx0), reserve):
-            n_sms = torch.cuda.get_device_properties(v.device).multi_processor_count
-            ctx0.set_sm_limit(max(8, n_sms - reserve) if reserve > 0 else 0)
-            self._sm_limit_set = (id(ctx0), reserve)
-        prev = self.__dict__.get("loss_ready")
-        loss0, h = self.layers[0].train_epoch_fwd(v, epoch, epochs, CD=self.cd_k, next_data=next_v,
-                                                  loss_out=None if loss_out is None else loss_out[0])
-        ready = torch.cuda.Event()
-        ready.record(main)
-        h.record_stream(side)
-        losses = [loss0]
-        with torch.cuda.stream(side):
-            side.wait_event(ready)
-            x = h
-            for i, rbm in enumerate(self.layers[1:], start=1):
-                loss, x = rbm.train_epoch_fwd(x, epoch, epochs, CD=self.cd_k,
-                                              loss_out=None if loss_out is None else loss_out[i])
-                if loss_out is None:
-                    loss.record_stream(main)
-                losses.append(loss)
-            done = torch.cuda.Event()
-            done.record(side)
-        self.loss_ready = done
-        del prev
+        if v.device.type == "cuda" and _dist.state() is None and getattr(self, "fused_step", True):
+            return self._train_step_fused(v, epoch, epochs, next_v, loss_out)
+        losses = []
+        for i, rbm in enumerate(self.layers):
+            loss, v = rbm.train_epoch_fwd(v, epoch, epochs, CD=self.cd_k, next_data=next_v if i == 0 else None,
+                                          loss_out=None if loss_out is None else loss_out[i])
+            losses.append(loss)
         return losses
+
+    def _train_step_fused(self, v, epoch, epochs, next_v, loss_out) -> List[torch.Tensor]:
+        """All layers of one minibatch through ONE library call (``imdbn_idbn_train_step``): the host pays for
+        one foreign call instead of one per layer plus the event / stream bookkeeping.
+
+        ``pipeline_layers = True``: layer 0 of minibatch t+1 does not depend on the upper layers of minibatch t
+        (they only consume layer 0's forward output), so the upper layers are enqueued on a side stream and
+        overlap the next layer-0 update.  The persistent tensor-core kernels of layer 0 are then confined to
+        ``num_sms - pipeline_reserve_sms`` SMs (their 197 KB CTAs would otherwise own every SM and the small
+        upper-layer kernels would queue behind them), and they are launched WITHOUT early dependent launch (a
+        dependent grid launched early parks its CTAs on exactly the SMs that were left free).  Measured on B200,
+        C2: 163 us per step against 174.5 us (device-resident); off by default because the end-to-end loop with
+        host batches does not gain.  Results are identical; ``sync()`` orders readers of the losses (which then
+        live in a ring reused every 8 steps) and of the upper layers' parameters."""
+        dev = v.device
+        n = len(self.layers)
+        B = v.shape[0]
+        nxt = _flat(next_v, dev) if next_v is not None else None
+        Bn = nxt.shape[0] if nxt is not None else 0
+        piped = bool(getattr(self, "pipeline_layers", False)) and n > 1
+        reserve = int(getattr(self, "pipeline_reserve_sms", 16)) if piped else 0
+        ctx0, s0 = L.context_for(v)
+        st = self.__dict__.get("_fused")
+        key = (B, Bn, dev, id(ctx0), piped, reserve, tuple(r.num_hidden for r in self.layers))
+        if st is None or st["key"] != key:
+            rings = [[torch.empty(B + (Bn if l == 0 else 0), r.num_hidden, device=dev, dtype=torch.float32)
+                      for l, r in enumerate(self.layers)] for _ in range(2)]
+            st = dict(key=key, rings=rings, parity=0, ctx1=None, s1=0, side=None,
+                      fwd=[(C.c_void_p * n)(*[t.data_ptr() for t in ring]) for ring in rings],
+                      rbms=(L.RbmStruct * n)(), upds=(L.UpdateStruct * n)(), rngs=(L.RngStruct * n)(),
+                      loss=(C.c_void_p * n)())
+            if piped:
+                side = self.__dict__.get("_side_stream")
+                if side is None:
+                    side = self._side_stream = torch.cuda.Stream(device=dev)
+                with torch.cuda.stream(side):
+                    st["ctx1"], st["s1"] = L.context_for(v)
+                st["side"] = side
+            n_sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            ctx0.set_sm_limit(max(8, n_sms - reserve) if reserve > 0 else 0)
+            self._fused = st
+        par = st["parity"]
+        st["parity"] = par ^ 1
+        if loss_out is None and piped:
+            # the upper layers write their losses from the side stream: use model-owned storage (a ring reused
+            # every 8 steps) instead of a fresh allocation the caching allocator might recycle too early
+            ring = st.setdefault("loss_ring", torch.zeros(8, n, device=dev, dtype=torch.float32))
+            st["loss_pos"] = (st.get("loss_pos", -1) + 1) % 8
+            loss_t = ring[st["loss_pos"]]
+        elif loss_out is None:
+            loss_t = torch.empty(n, device=dev, dtype=torch.float32)
+        else:
+            if loss_out.dtype != torch.float32 or loss_out.numel() != n or not (loss_out.is_cuda or loss_out.is_pinned()):
+                raise ValueError("loss_out must hold one fp32 element per layer on the device or in pinned host memory")
+            loss_t = loss_out
+        base = loss_t.data_ptr()
+        for l, rbm in enumerate(self.layers):
+            lr, mom = rbm._hyper(epoch)
+            st["rbms"][l] = rbm._struct(training=True)
+            st["upds"][l] = rbm._update_struct(lr, mom, B, rbm.sparsity)
+            st["rngs"][l] = rbm._next_rng()
+            st["loss"][l] = base + 4 * l
+        first = self.layers[0]
+        cached = first.__dict__.pop("_pos_cache", None)
+        pos_in = cached[1] if cached is not None and cached[0] == first._pos_key(v) else None
+        ctx1 = st["ctx1"]
+        ctx0.check(ctx0.lib.imdbn_idbn_train_step(
+            ctx0.handle, ctx1.handle if ctx1 is not None else None, n, st["rbms"], st["upds"], st["rngs"],
+            L.ptr(v), B, int(self.cd_k), L.ptr(pos_in), L.ptr(nxt), Bn, st["fwd"][par], st["loss"], par, s0,
+            st["s1"]), "imdbn_idbn_train_step")
+        for rbm in self.layers:
+            rbm._n_updates = getattr(rbm, "_n_updates", 0) + 1
+            rbm.__dict__.pop("_pos_cache", None)
+        if nxt is not None:
+            first._pos_cache = (first._pos_key(nxt), st["rings"][par][0][B:])
+        return [loss_t[l] for l in range(n)]
 
     def sync(self) -> None:
         """Make the current stream wait for the upper layers' side stream (call before reading losses or
         the upper layers' parameters on the current stream)."""
-        ev = self.__dict__.get("loss_ready")
-        if ev is not None:
-            torch.cuda.current_stream(self.device).wait_event(ev)
+        side = self.__dict__.get("_side_stream")
+        if side is not None:
+            torch.cuda.current_stream(self.device).wait_stream(side)
 
     def train(self, epochs: int, log_every_pca: int = 25, log_every_probe: int = 10):
         """Layer-interleaved CD training (idbn.py:179-305).  ``loss_history`` receives the mean
         loss of every epoch (one device->host read per epoch)."""
+        def keep(step_losses):
+            # pipelined layers: the losses live in a short ring written from the side stream -- copy them there
+            side = self.__dict__.get("_side_stream")
+            if side is None or not getattr(self, "pipeline_layers", False):
+                return step_losses
+            with torch.cuda.stream(side):
+                return [torch.stack(step_losses)]
+
         for epoch in range(int(epochs)):
             losses: List[torch.Tensor] = []
             cur = None
             for batch in prefetch_to_device(self.dataloader, self.device):
                 nxt = _flat(batch[0], self.device)
                 if cur is not None:
-                    losses.extend(self.train_step(cur, epoch, epochs, next_v=nxt))
+                    losses.extend(keep(self.train_step(cur, epoch, epochs, next_v=nxt)))
                 cur = nxt
             if cur is not None:
-                losses.extend(self.train_step(cur, epoch, epochs))
+                losses.extend(keep(self.train_step(cur, epoch, epochs)))
             self.sync()
             if losses:
-                mean_loss = float(torch.stack(losses).mean())
+                mean_loss = float(torch.cat([l.reshape(-1) for l in losses]).mean())
                 self.loss_history.append(mean_loss)
                 if self.wandb_run:
                     self.wandb_run.log({"idbn/loss": mean_loss, "epoch": epoch})
@@ -256,6 +302,12 @@ class iDBN:
         for rbm in reversed(self.layers):
             cur = rbm.backward(cur)
         return cur
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state.pop("_fused", None)            # library handles, ring buffers and the side stream are not model state
+        state.pop("_side_stream", None)
+        return state
 
     def save_model(self, path: str):
         """``{"layers": [...], "params": ...}`` pickle (idbn.py:361-373).  With peer-memory data parallelism

@@ -540,3 +540,46 @@ def test_train_step_writes_losses_into_pinned_host_memory(M, tmp_path, monkeypat
     assert torch.isfinite(runs[1]).all() and torch.equal(runs[0], runs[1])
     with pytest.raises(ValueError):
         m.layers[0].train_epoch_fwd(x[0], 0, 1, loss_out=torch.zeros(1))        # pageable host memory
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+def test_train_step_variants_are_identical(M, tmp_path, monkeypatch, prec):
+    """iDBN.train_step: per-layer calls, the single-call path (imdbn_idbn_train_step) and the pipelined
+    variant (upper layers on a side stream, layer-0 kernels confined to a subset of the SMs) give the same
+    parameters and losses bit for bit."""
+    monkeypatch.chdir(tmp_path)
+    M.set_precision(prec)
+    try:
+        p = dict(LEARNING_RATE=0.1, WEIGHT_PENALTY=1e-4, INIT_MOMENTUM=0.5, FINAL_MOMENTUM=0.95,
+                 LEARNING_RATE_DYNAMIC=True, SPARSITY=True, SPARSITY_FACTOR=0.1)
+        xs = [O.synthetic_images(32, 2000, seed=s).to(DEV) for s in range(6)]
+        results = []
+        for mode in ("layers", "fused", "pipelined"):
+            torch.manual_seed(0)
+            m = M.iDBN([2000, 600, 200, 64], dict(p), None, None, torch.device(DEV))
+            for i, l in enumerate(m.layers):
+                l.set_rng(5 + i, 0)
+            m.fused_step = mode != "layers"
+            m.pipeline_layers = mode == "pipelined"
+            m.pipeline_reserve_sms = 24
+            losses = []
+            for t in range(5):
+                step_losses = m.train_step(xs[t], t, 5, next_v=xs[t + 1])
+                m.sync()                                  # (pipelined: the upper layers' losses come from the side stream)
+                losses.append(torch.stack(step_losses))
+            m.sync()
+            torch.cuda.synchronize()
+            results.append((torch.stack(losses).cpu(), [l.W.detach().cpu().clone() for l in m.layers],
+                            [l.hid_bias.detach().cpu().clone() for l in m.layers]))
+            if mode == "pipelined":                       # the model still pickles (handles are dropped)
+                import pickle
+                pickle.loads(pickle.dumps(m.layers[0]))
+                assert "_fused" not in m.__getstate__()
+        for other in results[1:]:
+            assert torch.equal(results[0][0], other[0])
+            for a, b in zip(results[0][1], other[1]):
+                assert torch.equal(a, b)
+            for a, b in zip(results[0][2], other[2]):
+                assert torch.equal(a, b)
+    finally:
+        M.set_precision("fp32")
