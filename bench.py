@@ -252,12 +252,17 @@ def run_ours(args):
         if cur is not None:
             model.train_step(cur, 0, 1, loss_out=loss_host[off + i])
 
+    # K steps, three times; the MEDIAN repetition is reported (this loop includes the host: a single repetition
+    # is exposed to scheduling noise of the box), all three are listed in e2e.runs_ms
     e2e_loop(warm, 0)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_loop(steps, warm)
-    barrier()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    e2e_runs = []
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        e2e_loop(steps, warm)
+        barrier()
+        e2e_runs.append(max_over_ranks((time.perf_counter() - t0) * 1e3))
+    e2e_ms = sorted(e2e_runs)[1]
     e2e_val = world * BATCH * steps / (e2e_ms * 1e-3)
     assert torch.isfinite(loss_host[warm:]).all()
 
@@ -296,10 +301,13 @@ def run_ours(args):
         "config": {"workload": "C2 iDBN [10000,1500,500] CD-1 batch 64 per GPU (idbn.py:199-204)",
                    "global_batch": BATCH * world,
                    "parallelism": dp_desc,
+                   "layer_pipelining": (f"upper layers on a side stream, {args.pipeline_reserve} SMs left to them "
+                                        f"(iDBN.pipeline_layers; results bit-identical)"
+                                        if args.pipeline_reserve >= 0 and world == 1 else "off"),
                    "precision_mode": args.precision,
                    "l2": "state (W, W_m of both layers: 252 MB) + 164 MB of rotating inputs exceed the "
                          "126 MB L2; no explicit flush"},
-        "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": e2e_ms / steps,
+        "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": e2e_ms / steps, "runs_ms": e2e_runs,
                 "h2d_bytes_per_step": BATCH * LAYERS[0] * 4, "d2h_bytes_per_step": 4 * len(model.layers),
                 "d2h": "per-layer losses stored by the update kernels into mapped pinned host memory"},
         "gpu_launches": launches,
@@ -381,7 +389,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--pipeline-reserve", type=int, default=-1,
+    ap.add_argument("--pipeline-reserve", type=int, default=16,
                     help="SMs left to the upper layers, which then run on a side stream concurrently with the next "
                          "layer-0 update (-1 = layers run back to back on one stream)")
     args = ap.parse_args()

@@ -29,39 +29,62 @@ def _flat(x: torch.Tensor, device) -> torch.Tensor:
     return x.reshape(x.size(0), -1).float()
 
 
-def prefetch_to_device(loader: Iterable, device):
-    """Yield the loader's batches already on ``device``: batch i+1 is copied on a side stream while
-    the caller works on batch i.  Falls back to plain iteration on CPU devices."""
+def prefetch_to_device(loader: Iterable, device, ring: int = 4):
+    """Yield the loader's batches already on ``device``: batch i+1 is copied on a side stream while the caller
+    works on batch i.  Falls back to plain iteration on CPU devices.
+
+    The device copies live in a ring of ``ring`` preallocated buffers per tensor slot (no allocator traffic, no
+    ``record_stream`` bookkeeping in the steady state): a yielded tensor stays valid until ``ring - 1`` further
+    batches have been yielded, and the copy into a buffer first waits for the work the consumer had enqueued on
+    its stream when the buffer's previous occupant went out of use."""
     device = torch.device(device)
     if device.type != "cuda":
         for batch in loader:
             yield batch
         return
+    ring = max(3, int(ring))
     copy_stream = torch.cuda.Stream(device=device)
     main = torch.cuda.current_stream(device)
+    bufs = {}                      # (slot, position in the batch tuple) -> device buffer
+    fences = [None] * ring         # consumer-stream event recorded when the slot was handed out again
 
-    def stage(batch):
+    def stage(batch, n):
+        slot = n % ring
+        fence = torch.cuda.Event()
+        fence.record(main)         # everything the consumer enqueued so far (it is >= 2 batches behind this one)
+        fences[slot] = fence
         with torch.cuda.stream(copy_stream):
-            moved = tuple(b.to(device, non_blocking=True) if torch.is_tensor(b) else b for b in batch)
+            copy_stream.wait_event(fence)
+            moved = []
+            for pos, b in enumerate(batch):
+                if not torch.is_tensor(b):
+                    moved.append(b)
+                    continue
+                dst = bufs.get((slot, pos))
+                if dst is None or dst.shape != b.shape or dst.dtype != b.dtype:
+                    dst = torch.empty(b.shape, dtype=b.dtype, device=device)
+                    dst.record_stream(main)
+                    bufs[(slot, pos)] = dst
+                dst.copy_(b, non_blocking=True)
+                moved.append(dst)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
-        return moved, ev
+        return tuple(moved), ev
 
     it = iter(loader)
+    n = 0
     try:
-        cur = stage(next(it))
+        cur = stage(next(it), n)
     except StopIteration:
         return
     while cur is not None:
+        n += 1
         try:
-            nxt = stage(next(it))
+            nxt = stage(next(it), n)
         except StopIteration:
             nxt = None
         moved, ev = cur
         main.wait_event(ev)
-        for b in moved:
-            if torch.is_tensor(b):
-                b.record_stream(main)
         yield moved
         cur = nxt
 
@@ -284,6 +307,7 @@ class iDBN:
     @torch.no_grad()
     def represent(self, x: torch.Tensor, upto_layer: Optional[int] = None) -> torch.Tensor:
         """idbn.py:307-323."""
+        self.sync()
         v = _flat(x, self.device)
         L = len(self.layers) if upto_layer is None else max(0, min(len(self.layers), int(upto_layer)))
         for i in range(L):
@@ -298,6 +322,7 @@ class iDBN:
     @torch.no_grad()
     def decode(self, top: torch.Tensor) -> torch.Tensor:
         """idbn.py:346-359."""
+        self.sync()
         cur = top.to(self.device)
         for rbm in reversed(self.layers):
             cur = rbm.backward(cur)
@@ -312,6 +337,7 @@ class iDBN:
     def save_model(self, path: str):
         """``{"layers": [...], "params": ...}`` pickle (idbn.py:361-373).  With peer-memory data parallelism
         active this is a collective (every rank calls it; momenta slabs are gathered first)."""
+        self.sync()
         for l in self.layers:
             l.sync_momenta()
         with open(path, "wb") as f:
