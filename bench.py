@@ -216,6 +216,11 @@ def run_ours(args):
     def batch(i):
         return resident[i % N_DISTINCT_BATCHES]
 
+    # untimed setup: one pass over the distinct input buffers fills the library's TMA-descriptor cache (descriptors
+    # are keyed by buffer address; encoding them costs host time the first time a buffer is seen), then the W
+    # warm-up steps proper
+    for i in range(N_DISTINCT_BATCHES):
+        model.train_step(batch(i), 0, 1, next_v=batch(i + 1))
     for i in range(warm):
         model.train_step(batch(i), 0, 1, next_v=batch(i + 1))
     barrier()
@@ -267,7 +272,7 @@ def run_ours(args):
     assert torch.isfinite(loss_host[warm:]).all()
 
     # ---------------- roofline of the dominant kernel (layer-0 statistics + update), CUDA events
-    ctx, _ = L.context_for(model.layers[0].W)
+    ctx = (model.__dict__.get("_fused") or {}).get("ctx0") or L.context_for(model.layers[0].W)[0]   # layer 0's context
     ctx.profile(True)
     n_prof = min(steps, 20)
     for i in range(n_prof):
@@ -301,8 +306,10 @@ def run_ours(args):
         "config": {"workload": "C2 iDBN [10000,1500,500] CD-1 batch 64 per GPU (idbn.py:199-204)",
                    "global_batch": BATCH * world,
                    "parallelism": dp_desc,
-                   "layer_pipelining": (f"upper layers on a side stream, {args.pipeline_reserve} SMs left to them "
-                                        f"(iDBN.pipeline_layers; results bit-identical)"
+                   "layer_pipelining": (f"upper layers of minibatch t next to layer 0 of minibatch t+1 on disjoint SM "
+                                        f"partitions (CUDA green contexts, {args.pipeline_reserve} SMs for the upper "
+                                        f"layers; iDBN.pipeline_layers; same arithmetic, split-K order follows the "
+                                        f"partition sizes)"
                                         if args.pipeline_reserve >= 0 and world == 1 else "off"),
                    "precision_mode": args.precision,
                    "l2": "state (W, W_m of both layers: 252 MB) + 164 MB of rotating inputs exceed the "

@@ -149,7 +149,14 @@ int imdbn_idbn_train_step(imdbn_ctx* ctx0, imdbn_ctx* ctx1, int n_layers, const 
                           const imdbn_update* upds, const imdbn_rng* rngs, const float* data, int B, int k,
                           const float* pos_h_in, const float* next_data, int B_next, float* const* fwd_out,
                           float* const* loss_out, int buffer_set /* 0 | 1: which set fwd_out belongs to */,
-                          imdbn_stream stream0, imdbn_stream stream1);
+                          imdbn_stream stream0, imdbn_stream stream1,
+                          imdbn_stream caller_stream /* nullable: stream the inputs were produced on, if not stream0 */,
+                          int early_launch /* 0: layer 0 without programmatic dependent launch */);
+
+/* Two streams whose kernels run on DISJOINT sets of SMs (CUDA green contexts, created once per device): the small
+ * partition has >= small_sms SMs (multiples of 8), the big one the rest.  Used to train the upper layers of an
+ * iDBN next to the bottom layer without either side's early-launched grids squatting on the other's SMs. */
+int imdbn_sm_partition(int device, int small_sms, void** stream_big, void** stream_small, int* n_big, int* n_small);
 
 /* The same statistics without the update, for batches sharded over ranks: writes the local sums
  *   stats_out = [ dS (V*H) | dh (H) | dv (V) | pos_h column sum (H) | squared error (1) ]

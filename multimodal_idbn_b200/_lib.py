@@ -93,7 +93,8 @@ SIGNATURES = {
     "imdbn_apply_update": (_I, [_P, C.POINTER(RbmStruct), _P, C.POINTER(UpdateStruct), _P, _P]),
     "imdbn_set_sm_limit": (_I, [_P, _I]),
     "imdbn_idbn_train_step": (_I, [_P, _P, _I, C.POINTER(RbmStruct), C.POINTER(UpdateStruct), C.POINTER(RngStruct), _P, _I,
-                                   _I, _P, _P, _I, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _I, _P, _P]),
+                                   _I, _P, _P, _I, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _I, _P, _P, _P, _I]),
+    "imdbn_sm_partition": (_I, [_I, _I, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "imdbn_dp_update": (_I, [_P, C.POINTER(RbmStruct), C.POINTER(PeersStruct), C.POINTER(UpdateStruct), _P, _P]),
     "imdbn_class_free_energies": (_I, [_P, C.POINTER(RbmStruct), _P, _I, _I, _P, _P]),
     "imdbn_trace_img2txt": (_I, [_P, C.POINTER(RbmStruct), _P, _I, _I, _P, _I, _P, _P]),
@@ -220,6 +221,33 @@ def context_for(t: torch.Tensor) -> Tuple[Context, int]:
         _contexts[key] = ctx
     ctx.set_precision(_precision)
     return ctx, int(stream)
+
+
+_partitions = {}
+
+
+def sm_partition(device_index: int, small_sms: int):
+    """``(stream_big, stream_small, n_big, n_small)`` -- raw handles of two streams on disjoint SM sets (CUDA green
+    contexts, ``imdbn_sm_partition``), or None when the driver cannot provide them.  One partition per device."""
+    if device_index not in _partitions:
+        lib = load_library()
+        big, small = C.c_void_p(), C.c_void_p()
+        nb, ns = C.c_int(), C.c_int()
+        rc = lib.imdbn_sm_partition(int(device_index), int(small_sms), C.byref(big), C.byref(small), C.byref(nb),
+                                    C.byref(ns))
+        _partitions[device_index] = (big.value, small.value, nb.value, ns.value) if rc == 0 and big.value else None
+    return _partitions[device_index]
+
+
+def context_for_stream(device_index: int, stream_handle: int) -> "Context":
+    """Context bound to a raw stream handle (streams that torch did not create)."""
+    key = (device_index, int(stream_handle))
+    ctx = _contexts.get(key)
+    if ctx is None:
+        ctx = Context(device_index)
+        _contexts[key] = ctx
+    ctx.set_precision(_precision)
+    return ctx
 
 
 def total_launches() -> int:

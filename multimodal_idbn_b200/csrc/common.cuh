@@ -42,7 +42,7 @@ struct imdbn_ctx {
     bool stats_after_colstats = false;   // next tc statistics kernel directly follows k_colstats (see tc_stats.cuh)
     unsigned int* ticket = nullptr;   // device counter of the last-block reductions (self-resetting)
     // imdbn_idbn_train_step with a second context: cross-stream events (created lazily)
-    cudaEvent_t ev_ready = nullptr;
+    cudaEvent_t ev_ready = nullptr, ev_in = nullptr, ev_out = nullptr;
     cudaEvent_t ev_done[2] = {nullptr, nullptr};
 };
 

@@ -475,7 +475,8 @@ static bool cd_small_eligible(const imdbn_ctx* ctx, const imdbn_rbm* r, const fl
 static int cd_small(imdbn_ctx* ctx, const imdbn_rbm* r, const float* data, int B, int k,
                     const imdbn_update* upd, const imdbn_rng* rng, float* loss_out, cudaStream_t st,
                     const FwdTail* tail) {
-    const int V = r->V, H = r->H, G = ctx->num_sms;
+    // every CTA must be resident for the grid barriers: one CTA per SM of the partition this context may use
+    const int V = r->V, H = r->H, G = tc_sms(ctx);
     CdSmallArgs a{};
     a.W = r->W; a.Wm = r->Wm; a.hb = r->hb; a.hbm = r->hbm; a.vb = r->vb; a.vbm = r->vbm;
     a.V = V; a.H = H; a.data = data; a.B = B; a.k = k;
@@ -761,6 +762,8 @@ void imdbn_ctx_destroy(imdbn_ctx* ctx) {
     prof_clear(ctx);
     if (ctx->ticket) cudaFree(ctx->ticket);
     if (ctx->ev_ready) cudaEventDestroy(ctx->ev_ready);
+    if (ctx->ev_in) cudaEventDestroy(ctx->ev_in);
+    if (ctx->ev_out) cudaEventDestroy(ctx->ev_out);
     for (int i = 0; i < 2; ++i)
         if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
     if (ctx->arena.base) cudaFree(ctx->arena.base);
@@ -768,6 +771,10 @@ void imdbn_ctx_destroy(imdbn_ctx* ctx) {
 }
 
 const char* imdbn_last_error(imdbn_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int imdbn_sm_partition(int device, int small_sms, void** stream_big, void** stream_small, int* n_big, int* n_small) {
+    return sm_partition(device, small_sms, stream_big, stream_small, n_big, n_small);
+}
 
 int imdbn_set_sm_limit(imdbn_ctx* ctx, int n_sms) {
     IMDBN_ARG(ctx, ctx && n_sms >= 0);
@@ -901,10 +908,20 @@ int imdbn_cd_train_fwd(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* data, 
 int imdbn_idbn_train_step(imdbn_ctx* ctx0, imdbn_ctx* ctx1, int n_layers, const imdbn_rbm* rbms,
                           const imdbn_update* upds, const imdbn_rng* rngs, const float* data, int B, int k,
                           const float* pos_h_in, const float* next_data, int B_next, float* const* fwd_out,
-                          float* const* loss_out, int buffer_set, imdbn_stream stream0, imdbn_stream stream1) {
+                          float* const* loss_out, int buffer_set, imdbn_stream stream0, imdbn_stream stream1,
+                          imdbn_stream caller_stream, int early_launch) {
     IMDBN_ARG(ctx0, ctx0 && n_layers >= 1 && rbms && upds && rngs && data && fwd_out && loss_out && B > 0);
     IMDBN_ARG(ctx0, buffer_set == 0 || buffer_set == 1);
-    cudaStream_t s0 = (cudaStream_t)stream0, s1 = (cudaStream_t)stream1;
+    cudaStream_t s0 = (cudaStream_t)stream0, s1 = (cudaStream_t)stream1, sc = (cudaStream_t)caller_stream;
+    const bool foreign = caller_stream != nullptr && sc != s0;      // layer 0 runs on a stream other than the caller's
+    if (foreign) {
+        if (!ctx0->ev_in) {
+            IMDBN_CUDA(ctx0, cudaEventCreateWithFlags(&ctx0->ev_in, cudaEventDisableTiming));
+            IMDBN_CUDA(ctx0, cudaEventCreateWithFlags(&ctx0->ev_out, cudaEventDisableTiming));
+        }
+        IMDBN_CUDA(ctx0, cudaEventRecord(ctx0->ev_in, sc));          // inputs produced on the caller's stream
+        IMDBN_CUDA(ctx0, cudaStreamWaitEvent(s0, ctx0->ev_in, 0));
+    }
     const bool piped = ctx1 != nullptr && n_layers > 1;
     const int par = buffer_set;
     if (piped) {
@@ -920,11 +937,16 @@ int imdbn_idbn_train_step(imdbn_ctx* ctx0, imdbn_ctx* ctx1, int n_layers, const 
     }
     for (int l = 0; l < n_layers; ++l) IMDBN_ARG(ctx0, fwd_out[l] && upds[l].batch_global > 0);
     FwdTail t0{pos_h_in, next_data, next_data ? B_next : 0, fwd_out[0]};
-    static const bool keep_pdl = getenv("IMDBN_PIPE_PDL") != nullptr;
-    if (piped && !keep_pdl) pdl_early() = false;
+    // Without an SM partition an early-launched dependent grid parks its CTAs on the SMs that were meant for the
+    // other stream: the caller then asks for plain stream-ordered launches of layer 0.
+    if (piped && !early_launch) pdl_early() = false;
     int rc = cd_core(ctx0, &rbms[0], data, B, k, &upds[0], &rngs[0], loss_out[0], nullptr, s0, &t0);
     pdl_early() = true;
     if (rc) return rc;
+    if (foreign) {                                                    // the caller's stream sees layer 0's results
+        IMDBN_CUDA(ctx0, cudaEventRecord(ctx0->ev_out, s0));
+        IMDBN_CUDA(ctx0, cudaStreamWaitEvent(sc, ctx0->ev_out, 0));
+    }
     imdbn_ctx* cx = ctx0;
     cudaStream_t sx = s0;
     if (piped) {

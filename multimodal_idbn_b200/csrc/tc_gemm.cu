@@ -450,4 +450,63 @@ int tc_gemm_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* vp, const flo
     return 0;
 }
 
+// ---- SM partition (CUDA green contexts): two streams whose kernels run on disjoint sets of SMs ---------------
+namespace {
+struct SmPartition { bool tried = false; bool ok = false; CUstream big = nullptr, small_ = nullptr; int n_big = 0, n_small = 0; };
+SmPartition g_partitions[16];
+
+template <typename Fn>
+bool drv(const char* name, Fn* out) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn)
+        return false;
+    *out = reinterpret_cast<Fn>(fn);
+    return true;
+}
+}  // namespace
+
+int sm_partition(int device, int small_sms, void** stream_big, void** stream_small, int* n_big, int* n_small) {
+    if (device < 0 || device >= 16 || !stream_big || !stream_small || small_sms < 8) return -1;
+    SmPartition& P = g_partitions[device];
+    if (!P.tried) {
+        P.tried = true;
+        typedef CUresult (*FGetDev)(CUdevice*, int);
+        typedef CUresult (*FGetRes)(CUdevice, CUdevResource*, CUdevResourceType);
+        typedef CUresult (*FSplit)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int);
+        typedef CUresult (*FDesc)(CUdevResourceDesc*, CUdevResource*, unsigned int);
+        typedef CUresult (*FCreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int);
+        typedef CUresult (*FStream)(CUstream*, CUgreenCtx, unsigned int, int);
+        FGetDev fGetDev; FGetRes fGetRes; FSplit fSplit; FDesc fDesc; FCreate fCreate; FStream fStream;
+        if (cudaSetDevice(device) != cudaSuccess || cudaFree(0) != cudaSuccess) return -2;
+        if (!drv("cuDeviceGet", &fGetDev) || !drv("cuDeviceGetDevResource", &fGetRes) ||
+            !drv("cuDevSmResourceSplitByCount", &fSplit) || !drv("cuDevResourceGenerateDesc", &fDesc) ||
+            !drv("cuGreenCtxCreate", &fCreate) || !drv("cuGreenCtxStreamCreate", &fStream))
+            return -3;
+        CUdevice dev;
+        CUdevResource all, grp, rest;
+        unsigned int nb = 1;
+        CUdevResourceDesc d_small, d_big;
+        CUgreenCtx g_small, g_big;
+        if (fGetDev(&dev, device) != CUDA_SUCCESS || fGetRes(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return -4;
+        if (fSplit(&grp, &nb, &all, &rest, 0, (unsigned int)small_sms) != CUDA_SUCCESS || nb < 1) return -5;
+        if (fDesc(&d_small, &grp, 1) != CUDA_SUCCESS || fDesc(&d_big, &rest, 1) != CUDA_SUCCESS) return -6;
+        if (fCreate(&g_small, d_small, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS ||
+            fCreate(&g_big, d_big, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS)
+            return -7;
+        if (fStream(&P.small_, g_small, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS ||
+            fStream(&P.big, g_big, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS)
+            return -8;
+        P.n_small = (int)grp.sm.smCount;
+        P.n_big = (int)rest.sm.smCount;
+        P.ok = true;
+    }
+    if (!P.ok) return -9;
+    *stream_big = P.big; *stream_small = P.small_;
+    if (n_big) *n_big = P.n_big;
+    if (n_small) *n_small = P.n_small;
+    return 0;
+}
+
+
 }  // namespace imdbn

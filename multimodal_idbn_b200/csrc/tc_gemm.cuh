@@ -22,4 +22,7 @@ void tc_destroy(imdbn_ctx* ctx);
 SKPlan tc_plan(const imdbn_ctx* ctx, int M_total, int K_total);
 int tc_plan_max_slabs(const SKPlan& p, int M_total);
 
+// two streams on disjoint SM sets (CUDA green contexts); see imdbn_sm_partition in the public header
+int sm_partition(int device, int small_sms, void** stream_big, void** stream_small, int* n_big, int* n_small);
+
 }  // namespace imdbn

@@ -29,14 +29,24 @@ def _flat(x: torch.Tensor, device) -> torch.Tensor:
     return x.reshape(x.size(0), -1).float()
 
 
+# device staging buffers survive the generator (a new epoch reuses them instead of asking the allocator, whose
+# cudaMalloc would synchronise the device): per (device, ring) the buffers and an event recorded on the consumer's
+# stream when the previous generator finished
+_staging_cache = {}
+
+
 def prefetch_to_device(loader: Iterable, device, ring: int = 4):
     """Yield the loader's batches already on ``device``: batch i+1 is copied on a side stream while the caller
     works on batch i.  Falls back to plain iteration on CPU devices.
 
-    The device copies live in a ring of ``ring`` preallocated buffers per tensor slot (no allocator traffic, no
-    ``record_stream`` bookkeeping in the steady state): a yielded tensor stays valid until ``ring - 1`` further
-    batches have been yielded, and the copy into a buffer first waits for the work the consumer had enqueued on
-    its stream when the buffer's previous occupant went out of use."""
+    The device copies live in a ring of ``ring`` preallocated buffers per tensor slot that survives the generator
+    (no allocator traffic in the steady state and none at the start of the next epoch -- a cudaMalloc would
+    synchronise the device).  Contract for the consumer: a yielded tensor stays valid while the NEXT yielded batch
+    is being processed (one batch of lookahead, as ``iDBN.train`` uses it); the copy into a buffer is ordered,
+    by an event, after everything the consumer had enqueued on its stream when the copy was issued, and the
+    buffer's previous occupant is at least ``ring - 1`` batches old by then.
+    (A worker-thread variant was measured and dropped: 183 us per C2 step against 140-150 us -- the GIL hand-offs
+    cost more than the ~20 us of staging work they take off the consumer thread.)"""
     device = torch.device(device)
     if device.type != "cuda":
         for batch in loader:
@@ -45,14 +55,15 @@ def prefetch_to_device(loader: Iterable, device, ring: int = 4):
     ring = max(3, int(ring))
     copy_stream = torch.cuda.Stream(device=device)
     main = torch.cuda.current_stream(device)
-    bufs = {}                      # (slot, position in the batch tuple) -> device buffer
-    fences = [None] * ring         # consumer-stream event recorded when the slot was handed out again
+    cache_key = (device.index if device.index is not None else torch.cuda.current_device(), ring)
+    bufs, prev_end = _staging_cache.pop(cache_key, ({}, None))
+    if prev_end is not None:
+        copy_stream.wait_event(prev_end)           # the previous consumer's reads of these buffers
 
     def stage(batch, n):
         slot = n % ring
         fence = torch.cuda.Event()
         fence.record(main)         # everything the consumer enqueued so far (it is >= 2 batches behind this one)
-        fences[slot] = fence
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(fence)
             moved = []
@@ -74,19 +85,24 @@ def prefetch_to_device(loader: Iterable, device, ring: int = 4):
     it = iter(loader)
     n = 0
     try:
-        cur = stage(next(it), n)
-    except StopIteration:
-        return
-    while cur is not None:
-        n += 1
         try:
-            nxt = stage(next(it), n)
+            cur = stage(next(it), n)
         except StopIteration:
-            nxt = None
-        moved, ev = cur
-        main.wait_event(ev)
-        yield moved
-        cur = nxt
+            return
+        while cur is not None:
+            n += 1
+            try:
+                nxt = stage(next(it), n)
+            except StopIteration:
+                nxt = None
+            moved, ev = cur
+            main.wait_event(ev)
+            yield moved
+            cur = nxt
+    finally:
+        end = torch.cuda.Event()
+        end.record(main)
+        _staging_cache[cache_key] = (bufs, end)
 
 
 class iDBN:
@@ -197,14 +213,16 @@ class iDBN:
         one foreign call instead of one per layer plus the event / stream bookkeeping.
 
         ``pipeline_layers = True``: layer 0 of minibatch t+1 does not depend on the upper layers of minibatch t
-        (they only consume layer 0's forward output), so the upper layers are enqueued on a side stream and
-        overlap the next layer-0 update.  The persistent tensor-core kernels of layer 0 are then confined to
-        ``num_sms - pipeline_reserve_sms`` SMs (their 197 KB CTAs would otherwise own every SM and the small
-        upper-layer kernels would queue behind them), and they are launched WITHOUT early dependent launch (a
-        dependent grid launched early parks its CTAs on exactly the SMs that were left free).  Measured on B200,
-        C2: 163 us per step against 174.5 us (device-resident); off by default because the end-to-end loop with
-        host batches does not gain.  Results are identical; ``sync()`` orders readers of the losses (which then
-        live in a ring reused every 8 steps) and of the upper layers' parameters."""
+        (they only consume layer 0's forward output), so the two run CONCURRENTLY on disjoint SM partitions
+        (CUDA green contexts, ``imdbn_sm_partition``: ``pipeline_reserve_sms`` SMs for the upper layers, the rest
+        for layer 0; every persistent grid is sized to its partition).  Without partitions (driver too old,
+        ``pipeline_partition = False``) the upper layers go to an ordinary side stream, layer 0's grids are capped
+        at ``num_sms - pipeline_reserve_sms`` and launched without early dependent launch (an early-launched grid
+        parks its CTAs on exactly the SMs that were left free).  Measured on B200, C2: 141-150 us per step with
+        partitions, 165 us with the fallback, 174 us unpipelined.  The arithmetic is the same; the split-K
+        summation order follows the grid sizes, so results agree with the unpipelined run to rounding.
+        ``sync()`` orders readers of the losses (which then live in a ring reused every 8 steps) and of the
+        parameters on the caller's stream."""
         dev = v.device
         n = len(self.layers)
         B = v.shape[0]
@@ -212,26 +230,39 @@ class iDBN:
         Bn = nxt.shape[0] if nxt is not None else 0
         piped = bool(getattr(self, "pipeline_layers", False)) and n > 1
         reserve = int(getattr(self, "pipeline_reserve_sms", 16)) if piped else 0
-        ctx0, s0 = L.context_for(v)
+        ctx_c, s_caller = L.context_for(v)
         st = self.__dict__.get("_fused")
-        key = (B, Bn, dev, id(ctx0), piped, reserve, tuple(r.num_hidden for r in self.layers))
+        key = (B, Bn, dev, s_caller, piped, reserve, tuple(r.num_hidden for r in self.layers))
         if st is None or st["key"] != key:
             rings = [[torch.empty(B + (Bn if l == 0 else 0), r.num_hidden, device=dev, dtype=torch.float32)
                       for l, r in enumerate(self.layers)] for _ in range(2)]
-            st = dict(key=key, rings=rings, parity=0, ctx1=None, s1=0, side=None,
+            st = dict(key=key, rings=rings, parity=0, ctx0=ctx_c, s0=s_caller, ctx1=None, s1=0, early=1, streams=[],
                       fwd=[(C.c_void_p * n)(*[t.data_ptr() for t in ring]) for ring in rings],
                       rbms=(L.RbmStruct * n)(), upds=(L.UpdateStruct * n)(), rngs=(L.RngStruct * n)(),
                       loss=(C.c_void_p * n)())
-            if piped:
-                side = self.__dict__.get("_side_stream")
-                if side is None:
-                    side = self._side_stream = torch.cuda.Stream(device=dev)
+            n_sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            idx = dev.index if dev.index is not None else torch.cuda.current_device()
+            part = L.sm_partition(idx, reserve) if piped and reserve >= 8 and getattr(self, "pipeline_partition", True) else None
+            if part is not None:
+                # layer 0 and the upper layers on two streams with DISJOINT SMs (green contexts): early dependent
+                # launch stays on, every grid is sized to its own partition
+                big, small, n_big, n_small = part
+                st["ctx0"], st["s0"] = L.context_for_stream(idx, big), big
+                st["ctx1"], st["s1"] = L.context_for_stream(idx, small), small
+                st["ctx0"].set_sm_limit(n_big)
+                st["ctx1"].set_sm_limit(n_small)
+                st["streams"] = [torch.cuda.ExternalStream(big, device=dev), torch.cuda.ExternalStream(small, device=dev)]
+            elif piped:
+                side = torch.cuda.Stream(device=dev)
                 with torch.cuda.stream(side):
                     st["ctx1"], st["s1"] = L.context_for(v)
-                st["side"] = side
-            n_sms = torch.cuda.get_device_properties(dev).multi_processor_count
-            ctx0.set_sm_limit(max(8, n_sms - reserve) if reserve > 0 else 0)
+                st["streams"] = [side]
+                st["early"] = 0
+                ctx_c.set_sm_limit(max(8, n_sms - reserve) if reserve > 0 else 0)
+            else:
+                ctx_c.set_sm_limit(0)
             self._fused = st
+            self._side_stream = st["streams"]
         par = st["parity"]
         st["parity"] = par ^ 1
         if loss_out is None and piped:
@@ -256,11 +287,11 @@ class iDBN:
         first = self.layers[0]
         cached = first.__dict__.pop("_pos_cache", None)
         pos_in = cached[1] if cached is not None and cached[0] == first._pos_key(v) else None
-        ctx1 = st["ctx1"]
+        ctx0, ctx1 = st["ctx0"], st["ctx1"]
         ctx0.check(ctx0.lib.imdbn_idbn_train_step(
             ctx0.handle, ctx1.handle if ctx1 is not None else None, n, st["rbms"], st["upds"], st["rngs"],
-            L.ptr(v), B, int(self.cd_k), L.ptr(pos_in), L.ptr(nxt), Bn, st["fwd"][par], st["loss"], par, s0,
-            st["s1"]), "imdbn_idbn_train_step")
+            L.ptr(v), B, int(self.cd_k), L.ptr(pos_in), L.ptr(nxt), Bn, st["fwd"][par], st["loss"], par, st["s0"],
+            st["s1"], s_caller, st["early"]), "imdbn_idbn_train_step")
         for rbm in self.layers:
             rbm._n_updates = getattr(rbm, "_n_updates", 0) + 1
             rbm.__dict__.pop("_pos_cache", None)
@@ -271,8 +302,7 @@ class iDBN:
     def sync(self) -> None:
         """Make the current stream wait for the upper layers' side stream (call before reading losses or
         the upper layers' parameters on the current stream)."""
-        side = self.__dict__.get("_side_stream")
-        if side is not None:
+        for side in self.__dict__.get("_side_stream") or ():
             torch.cuda.current_stream(self.device).wait_stream(side)
 
     def train(self, epochs: int, log_every_pca: int = 25, log_every_probe: int = 10):
@@ -280,10 +310,10 @@ class iDBN:
         loss of every epoch (one device->host read per epoch)."""
         def keep(step_losses):
             # pipelined layers: the losses live in a short ring written from the side stream -- copy them there
-            side = self.__dict__.get("_side_stream")
-            if side is None or not getattr(self, "pipeline_layers", False):
+            sides = self.__dict__.get("_side_stream")
+            if not sides or not getattr(self, "pipeline_layers", False):
                 return step_losses
-            with torch.cuda.stream(side):
+            with torch.cuda.stream(sides[-1]):
                 return [torch.stack(step_losses)]
 
         for epoch in range(int(epochs)):

@@ -545,8 +545,8 @@ def test_train_step_writes_losses_into_pinned_host_memory(M, tmp_path, monkeypat
 @pytest.mark.parametrize("prec", ["fp32", "tf32"])
 def test_train_step_variants_are_identical(M, tmp_path, monkeypatch, prec):
     """iDBN.train_step: per-layer calls, the single-call path (imdbn_idbn_train_step) and the pipelined
-    variant (upper layers on a side stream, layer-0 kernels confined to a subset of the SMs) give the same
-    parameters and losses bit for bit."""
+    variant (upper layers next to the following layer-0 update on disjoint SM partitions) give the same
+    parameters and losses."""
     monkeypatch.chdir(tmp_path)
     M.set_precision(prec)
     try:
@@ -575,11 +575,15 @@ def test_train_step_variants_are_identical(M, tmp_path, monkeypatch, prec):
                 import pickle
                 pickle.loads(pickle.dumps(m.layers[0]))
                 assert "_fused" not in m.__getstate__()
-        for other in results[1:]:
-            assert torch.equal(results[0][0], other[0])
-            for a, b in zip(results[0][1], other[1]):
-                assert torch.equal(a, b)
-            for a, b in zip(results[0][2], other[2]):
-                assert torch.equal(a, b)
+        # one call per layer vs one call per minibatch: the same launches, bit for bit
+        assert torch.equal(results[0][0], results[1][0])
+        for a, b in zip(results[0][1] + results[0][2], results[1][1] + results[1][2]):
+            assert torch.equal(a, b)
+        # pipelined on an SM partition: the grids (hence the split-K summation order) follow the partition sizes,
+        # so the results agree to rounding, not bitwise
+        tol = dict(rtol=2e-4, atol=2e-6) if prec == "fp32" else dict(rtol=5e-3, atol=1e-4)
+        torch.testing.assert_close(results[2][0], results[0][0], **tol)
+        for a, b in zip(results[0][1] + results[0][2], results[2][1] + results[2][2]):
+            torch.testing.assert_close(b, a, **tol)
     finally:
         M.set_precision("fp32")
