@@ -308,6 +308,19 @@ class iDBN:
     def train(self, epochs: int, log_every_pca: int = 25, log_every_probe: int = 10):
         """Layer-interleaved CD training (idbn.py:179-305).  ``loss_history`` receives the mean
         loss of every epoch (one device->host read per epoch)."""
+        # train() owns the loop and joins the streams at the end of every epoch, so it pipelines the layers unless
+        # told otherwise (pipeline_layers = False); direct train_step callers opt in explicitly
+        auto = getattr(self, "pipeline_layers", None) is None
+        if auto:
+            self.pipeline_layers = (self.device.type == "cuda" and len(self.layers) > 1 and _dist.state() is None)
+        try:
+            self._train_epochs(epochs)
+        finally:
+            self.sync()
+            if auto:
+                self.pipeline_layers = None
+
+    def _train_epochs(self, epochs: int) -> None:
         def keep(step_losses):
             # pipelined layers: the losses live in a short ring written from the side stream -- copy them there
             sides = self.__dict__.get("_side_stream")
