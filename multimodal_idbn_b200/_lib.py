@@ -229,6 +229,10 @@ _partitions = {}
 def sm_partition(device_index: int, small_sms: int):
     """``(stream_big, stream_small, n_big, n_small)`` -- raw handles of two streams on disjoint SM sets (CUDA green
     contexts, ``imdbn_sm_partition``), or None when the driver cannot provide them.  One partition per device."""
+    # Nsight Compute cannot profile kernels of green contexts ("Failed to prepare kernel for profiling"): profiling
+    # runs use IMDBN_NO_PARTITION=1 (layer pipelining then falls back to an ordinary side stream)
+    if os.environ.get("IMDBN_NO_PARTITION") or os.environ.get("CUDA_INJECTION64_PATH"):
+        return None
     if device_index not in _partitions:
         lib = load_library()
         big, small = C.c_void_p(), C.c_void_p()
