@@ -347,7 +347,7 @@ def chain_steps_metric(M, dev, n_chains, steps=50):
     mu = torch.rand(n_chains, Dz, device=dev)
     out = {"chains": n_chains, "steps": steps}
     for name, fn in (("img2txt_cond_gibbs", lambda: r.conditional_gibbs(vk1, km1, n_steps=steps, clamp_prefix=Dz)),
-                     ("txt2img_noisy_mf", lambda: r.noisy_meanfield_annealed(vk2, km2, n_steps=steps))):
+                     ("txt2img_noisy_mf", lambda: r.noisy_meanfield_annealed(vk2, km2, n_steps=steps, clamp_suffix=Dz))):
         r._mu_pull = {"mu_k": mu, "eta0": 0.15} if name.startswith("txt2img") else None
         fn(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -227,6 +227,10 @@ typedef struct {
     int32_t clamp_prefix;     /* >= 0: the caller promises known_mask == 1 exactly on columns
                                * [0, clamp_prefix) and 0 elsewhere (enables the label-only fast path
                                * of IMG->TXT inference); -1: arbitrary mask */
+    int32_t clamp_suffix;     /* >= 0: the caller promises known_mask == 1 exactly on columns [clamp_suffix, V)
+                               * and 0 elsewhere (TXT->IMG inference, imdbn.py:431-433): the large-batch chain then
+                               * skips the mask / known-value loads of the free columns and all work on the clamped
+                               * ones (their noise draws never reach an output); -1: arbitrary mask */
 } imdbn_chain;
 
 /* RBM.noisy_meanfield_annealed (rbm.py:300-367) / RBM.conditional_gibbs (rbm.py:369-400) /

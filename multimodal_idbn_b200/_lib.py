@@ -56,7 +56,8 @@ class ChainStruct(C.Structure):
                 ("T", c_float_p), ("sigma", c_float_p), ("eta", c_float_p),
                 ("mu", C.c_void_p), ("Dz", C.c_int32),
                 ("sample_h", C.c_int32), ("sample_v", C.c_int32),
-                ("final_free_sweep", C.c_int32), ("draw0", C.c_uint32), ("clamp_prefix", C.c_int32)]
+                ("final_free_sweep", C.c_int32), ("draw0", C.c_uint32), ("clamp_prefix", C.c_int32),
+                ("clamp_suffix", C.c_int32)]
 
 
 class ClampedCfgStruct(C.Structure):

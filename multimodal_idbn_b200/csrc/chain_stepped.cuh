@@ -50,6 +50,7 @@ struct ChainPost {
     int free_sweep;                        // 1: return the un-clamped probabilities (rbm.py:400)
     float* vprob_out;                      // nullable: un-clamped probabilities of this sweep
     Groups gr;
+    int clamp_from;                        // >= 0: known_mask is 1 exactly on columns >= clamp_from (caller's promise)
 };
 
 // logits = (sum_s part + vb)/T + sigma*N; non-group columns: sigmoid, mu-pull, re-clamp -> v_out;

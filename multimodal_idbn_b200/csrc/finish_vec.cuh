@@ -89,6 +89,13 @@ k_finish_down4(const float* __restrict__ part, int splits, SKPlan sk, int B, int
     for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const unsigned b = idx / q_per_row, c = (idx - b * q_per_row) << 2;
         const size_t i = (size_t)b * V + c;
+        // block mask promised by the caller: clamped columns only copy the known value (their logits, noise and
+        // softmax never reach an output), free columns need neither the mask nor the known values
+        const bool block_mask = cp.enabled && po.clamp_from >= 0 && !po.free_sweep && po.vprob_out == nullptr;
+        if (block_mask && (int)c >= po.clamp_from) {
+            *reinterpret_cast<float4*>(p_out + i) = *reinterpret_cast<const float4*>(po.vk + i);
+            continue;
+        }
         const int ns = finish_nslabs(sk, splits, c);
         const float4 a4 = sum_slabs4(part, ns, n, i);
         const float4 b4 = *reinterpret_cast<const float4*>(vb + c);
@@ -116,8 +123,8 @@ k_finish_down4(const float* __restrict__ part, int splits, SKPlan sk, int B, int
             *reinterpret_cast<float4*>(logits_out + i) = make_float4(x[0], x[1], x[2], x[3]);
             continue;
         }
-        float4 k4 = make_float4(0, 0, 0, 0), m4 = make_float4(1, 1, 1, 1);
-        if (!po.free_sweep) {
+        float4 k4 = make_float4(0, 0, 0, 0), m4 = make_float4(0, 0, 0, 0);     // (free column: v = p)
+        if (!po.free_sweep && !block_mask) {
             k4 = *reinterpret_cast<const float4*>(po.vk + i);
             m4 = *reinterpret_cast<const float4*>(po.km + i);
         }
@@ -128,7 +135,7 @@ k_finish_down4(const float* __restrict__ part, int splits, SKPlan sk, int B, int
             p[e] = sigmoid_t<FAST>(x[e]);
             if (po.mu && (int)(c + e) < po.Dz)
                 p[e] = add_rn(mul_rn(1.0f - po.eta, p[e]), mul_rn(po.eta, po.mu[(size_t)b * po.Dz + c + e]));
-            v[e] = po.free_sweep ? p[e] : clampmix(p[e], kk[e], mm[e]);
+            v[e] = (po.free_sweep || block_mask) ? p[e] : clampmix(p[e], kk[e], mm[e]);
         }
         if (po.vprob_out) *reinterpret_cast<float4*>(po.vprob_out + i) = make_float4(p[0], p[1], p[2], p[3]);
         *reinterpret_cast<float4*>(p_out + i) = make_float4(v[0], v[1], v[2], v[3]);

@@ -311,6 +311,23 @@ int run_chain_stepped(imdbn_ctx* ctx, const imdbn_rbm* r, const imdbn_chain* ch,
         po.free_sweep = free_sweep ? 1 : 0;
         po.vprob_out = (t == total - 1) ? vprob_out : nullptr;
         po.gr = gr;
+        // block-mask promise (TXT->IMG): honoured on the vector path when no softmax group straddles the boundary
+        po.clamp_from = -1;
+        bool groups_clamped = false;
+        if (vec && ch->clamp_suffix >= 0 && ch->clamp_suffix < V && ch->clamp_suffix % 4 == 0) {
+            int n_clamped = 0, n_free = 0, n_straddle = 0;
+            for (int g = 0; g < gr.n; ++g) {
+                if (gr.s[g] >= ch->clamp_suffix) ++n_clamped;
+                else if (gr.e[g] <= ch->clamp_suffix) ++n_free;
+                else ++n_straddle;
+            }
+            // all softmax groups on one side of the boundary (the group kernel must not read logits that the
+            // finish skipped)
+            if (n_straddle == 0 && (n_clamped == 0 || n_free == 0)) {
+                po.clamp_from = ch->clamp_suffix;
+                groups_clamped = n_free == 0 && !free_sweep && po.vprob_out == nullptr;
+            }
+        }
         if (vec) {
             ChainPost4 cp{}; cp.enabled = 1; cp.po = po;
             IMDBN_CUDA(ctx, launch_pdl(k_finish_down4<true>, dim3(vec_blocks((size_t)B * (V / 4), ctx->num_sms)), dim3(256),
@@ -321,7 +338,7 @@ int run_chain_stepped(imdbn_ctx* ctx, const imdbn_rbm* r, const imdbn_chain* ch,
                                        T, sig, key, d_v, po, lg, v));
         }
         ctx->launches++;
-        if (gr.n) {
+        if (gr.n && !groups_clamped) {             // (softmax groups inside the clamped block are overwritten anyway)
             IMDBN_CUDA(ctx, launch_pdl(k_chain_groups, dim3((B * gr.n * 32 + 127) / 128), dim3(128), 0, st, lg, B,
                                        V, po, v));
             ctx->launches++;

@@ -225,14 +225,14 @@ class iMDBN(nn.Module):
             jr._mu_pull = None
         v_chain = jr.noisy_meanfield_annealed(v_known=v_known, known_mask=km, n_steps=steps,
                                               T0=3.0, T1=1.0, sigma0=0.9, hot_frac=0.7,
-                                              sharpen_last=3, T_cold_plus=0.9)
+                                              sharpen_last=3, T_cold_plus=0.9, clamp_suffix=Dz)
         n_ref = int(self.N_CANDIDATES) - 1
         if hasattr(jr, "free_energy"):
             cands = [v_chain]
             for _ in range(n_ref):
                 cands.append(jr.noisy_meanfield_annealed(
                     v_known=cands[-1], known_mask=km, n_steps=1, T0=0.9, T1=0.9, sigma0=0.0,
-                    hot_frac=0.0, sharpen_last=0, T_cold_plus=0.9))
+                    hot_frac=0.0, sharpen_last=0, T_cold_plus=0.9, clamp_suffix=Dz))
             stack = torch.stack(cands, dim=0).contiguous()
             Fe = torch.stack([jr.free_energy(c) for c in cands], dim=0).contiguous()
             v_pick = torch.empty_like(v_chain)

@@ -392,7 +392,7 @@ class RBM(nn.Module):
     # ------------------------------------------------------------------ conditional inference
     def _run_chain(self, kind, v_known, known_mask, n_steps, tables=None, mu=None, sample_h=False,
                    sample_v=False, final_free=False, v_init=None, draw0=0, rng=None,
-                   want_vprob=False, clamp_prefix=-1):
+                   want_vprob=False, clamp_prefix=-1, clamp_suffix=-1):
         vk = self._in(v_known, self.num_visible)
         km = self._in(known_mask, self.num_visible)
         if km.shape != vk.shape:
@@ -421,6 +421,7 @@ class RBM(nn.Module):
         ch.sample_h, ch.sample_v, ch.final_free_sweep = int(sample_h), int(sample_v), int(final_free)
         ch.draw0 = draw0 & 0xFFFFFFFF
         ch.clamp_prefix = int(clamp_prefix)
+        ch.clamp_suffix = int(clamp_suffix)
         out = torch.empty_like(vk)
         vprob = torch.empty_like(vk) if want_vprob else None
         rs = self._struct()
@@ -433,10 +434,12 @@ class RBM(nn.Module):
     def noisy_meanfield_annealed(self, v_known: torch.Tensor, known_mask: torch.Tensor,
                                  n_steps: int = 72, T0: float = 3.0, T1: float = 1.0,
                                  sigma0: float = 0.9, hot_frac: float = 0.7, sharpen_last: int = 3,
-                                 T_cold_plus: float = 0.9):
+                                 T_cold_plus: float = 0.9, *, clamp_suffix: int = -1):
         """Noisy mean-field annealing with optional mu-pull (``self._mu_pull``), rbm.py:300-367.
         The whole chain is one persistent kernel.  ``hot_frac`` is accepted and, as in the
-        reference, has no effect.  Draws: 0 = U[B,V] init; step t: 1+2t = N[B,H], 2+2t = N[B,V]."""
+        reference, has no effect.  Draws: 0 = U[B,V] init; step t: 1+2t = N[B,H], 2+2t = N[B,V].
+        ``clamp_suffix = Dz`` (keyword-only extension) is the caller's promise that ``known_mask`` is 1 on
+        exactly the columns from Dz on (TXT->IMG inference): the large-batch chain then does no work on them."""
         n = int(n_steps)
         Ts, Ss, Es = [], [], []
         pull = getattr(self, "_mu_pull", None)
@@ -448,7 +451,7 @@ class RBM(nn.Module):
             frac = max(0.0, 1.0 - (t / max(1, n - 1)))
             Ts.append(max(1e-6, Tt)); Ss.append(sigma0 * frac); Es.append(eta0 * frac)
         return self._run_chain(L.CHAIN_NOISY_MF, v_known, known_mask, n, tables=(Ts, Ss, Es),
-                               mu=pull["mu_k"] if pull is not None else None)
+                               mu=pull["mu_k"] if pull is not None else None, clamp_suffix=clamp_suffix)
 
     @torch.no_grad()
     def conditional_gibbs(self, v_known: torch.Tensor, known_mask: torch.Tensor, n_steps: int = 30,

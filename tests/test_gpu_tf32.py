@@ -135,3 +135,31 @@ def test_large_batch_chains_on_tensor_cores(M):
     out = r.conditional_gibbs(vk.to(DEV), km.to(DEV), n_steps=20)
     torch.testing.assert_close(out.cpu(), ref, rtol=0, atol=3e-3)
     assert torch.allclose(out[:, Dz:].sum(1).cpu(), torch.ones(B), atol=1e-4)
+
+
+def test_block_mask_hint_gives_identical_chains():
+    """TXT->IMG noisy mean-field at a batch that takes the stepped tensor-core path: the clamp_suffix promise
+    (no work on the clamped label block, no mask loads on the free block) must not change a single value --
+    the random field is counter-addressed, so skipping the draws of clamped units shifts nothing."""
+    import multimodal_idbn_b200 as M
+    M.set_precision("tf32")
+    try:
+        V, H, Dz, K, B = 532, 256, 500, 32, 1024
+        torch.manual_seed(0)
+        r = M.RBM(V, H, 0.04, 1e-4, 0.5, softmax_groups=[(Dz, V)]).to(DEV)
+        with torch.no_grad():
+            r.W.data.mul_(4.0)
+        y = torch.nn.functional.one_hot(torch.randint(0, K, (B,)), K).float().to(DEV)
+        vk = torch.zeros(B, V, device=DEV); km = torch.zeros_like(vk); vk[:, Dz:] = y; km[:, Dz:] = 1
+        r._mu_pull = {"mu_k": torch.rand(B, Dz, device=DEV), "eta0": 0.15}
+        outs = []
+        for hint in (-1, Dz):
+            r.set_rng(77, 0)
+            outs.append(r.noisy_meanfield_annealed(vk, km, n_steps=7, clamp_suffix=hint))
+            r.set_rng(77, 0)
+            outs.append(r.noisy_meanfield_annealed(vk, km, n_steps=1, T0=0.9, T1=0.9, sigma0=0.0, sharpen_last=0,
+                                                   clamp_suffix=hint))
+        assert torch.equal(outs[0], outs[2]) and torch.equal(outs[1], outs[3])
+        assert torch.equal(outs[2][:, Dz:], y)
+    finally:
+        M.set_precision("fp32")
