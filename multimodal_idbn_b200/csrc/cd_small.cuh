@@ -267,11 +267,12 @@ __device__ void cds_finish(const CdSmallArgs& a, int nslab, int rows, int N, con
         p.z = sigmoidf_ref(add_rn(x.z, b.z)); p.w = sigmoidf_ref(add_rn(x.w, b.w));
         if (p_out) *reinterpret_cast<float4*>(p_out + o) = p;
         if (s_out) {
+            const float4 u4 = rf_uniform4(a.key, draw, row, c);     // one Philox call per quad
             float4 sv;
-            sv.x = p.x > rf_uniform(a.key, draw, row, c) ? 1.f : 0.f;
-            sv.y = p.y > rf_uniform(a.key, draw, row, c + 1) ? 1.f : 0.f;
-            sv.z = p.z > rf_uniform(a.key, draw, row, c + 2) ? 1.f : 0.f;
-            sv.w = p.w > rf_uniform(a.key, draw, row, c + 3) ? 1.f : 0.f;
+            sv.x = p.x > u4.x ? 1.f : 0.f;
+            sv.y = p.y > u4.y ? 1.f : 0.f;
+            sv.z = p.z > u4.z ? 1.f : 0.f;
+            sv.w = p.w > u4.w ? 1.f : 0.f;
             *reinterpret_cast<float4*>(s_out + o) = sv;
         }
     }

@@ -16,10 +16,6 @@ __device__ __forceinline__ float sigmoid_t(float x) {
     return sigmoidf_ref(x);
 }
 template <bool FAST>
-__device__ __forceinline__ float normal_t(const RngKey& k, uint32_t draw, uint32_t row, uint32_t col) {
-    return FAST ? rf_normal_fast(k, draw, row, col) : rf_normal(k, draw, row, col);
-}
-template <bool FAST>
 __device__ __forceinline__ float div_t(float x, float T, float invT) { return FAST ? x * invT : div_by(x, T, invT); }
 
 __device__ __forceinline__ float4 sum_slabs4(const float* __restrict__ part, int ns, size_t stride, size_t i) {
@@ -56,13 +52,21 @@ k_finish_up4(const float* __restrict__ part, int splits, SKPlan sk, int B, int H
         const float4 a4 = sum_slabs4(part, ns, n, i);
         const float4 b4 = *reinterpret_cast<const float4*>(hb + j);
         const float a[4] = {a4.x, a4.y, a4.z, a4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
-        float p[4], s[4];
+        float p[4], s[4], nz[4] = {0.f, 0.f, 0.f, 0.f}, un[4] = {0.f, 0.f, 0.f, 0.f};
+        if (sigma > 0.0f) {                      // two Philox calls for the four normals of this quad
+            const float2 n0 = rf_normal2_t<FAST>(key, draw_n, b, j), n1 = rf_normal2_t<FAST>(key, draw_n, b, j + 2);
+            nz[0] = n0.x; nz[1] = n0.y; nz[2] = n1.x; nz[3] = n1.y;
+        }
+        if (s_out) {                             // one Philox call for the four uniforms
+            const float4 u4 = rf_uniform4(key, draw_u, b, j);
+            un[0] = u4.x; un[1] = u4.y; un[2] = u4.z; un[3] = u4.w;
+        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             float x = div_t<FAST>(add_rn(a[e], bb[e]), T, invT);
-            if (sigma > 0.0f) x = add_rn(x, mul_rn(normal_t<FAST>(key, draw_n, b, j + e), sigma));
+            if (sigma > 0.0f) x = add_rn(x, mul_rn(nz[e], sigma));
             p[e] = sigmoid_t<FAST>(x);
-            if (s_out) s[e] = (p[e] > rf_uniform(key, draw_u, b, j + e)) ? 1.0f : 0.0f;
+            if (s_out) s[e] = (p[e] > un[e]) ? 1.0f : 0.0f;
         }
         if (p_out) *reinterpret_cast<float4*>(p_out + i) = make_float4(p[0], p[1], p[2], p[3]);
         if (s_out) *reinterpret_cast<float4*>(s_out + i) = make_float4(s[0], s[1], s[2], s[3]);
@@ -100,17 +104,26 @@ k_finish_down4(const float* __restrict__ part, int splits, SKPlan sk, int B, int
         const float4 a4 = sum_slabs4(part, ns, n, i);
         const float4 b4 = *reinterpret_cast<const float4*>(vb + c);
         const float a[4] = {a4.x, a4.y, a4.z, a4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
-        float x[4], p[4], s[4];
+        float x[4], p[4], s[4], nz[4] = {0.f, 0.f, 0.f, 0.f};
+        if (sigma > 0.0f) {
+            const float2 n0 = rf_normal2_t<FAST>(key, draw_n, b, c), n1 = rf_normal2_t<FAST>(key, draw_n, b, c + 2);
+            nz[0] = n0.x; nz[1] = n0.y; nz[2] = n1.x; nz[3] = n1.y;
+        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             x[e] = div_t<FAST>(add_rn(a[e], bb[e]), T, invT);
-            if (sigma > 0.0f) x[e] = add_rn(x[e], mul_rn(normal_t<FAST>(key, draw_n, b, c + e), sigma));
+            if (sigma > 0.0f) x[e] = add_rn(x[e], mul_rn(nz[e], sigma));
         }
         if (!cp.enabled) {
+            float un[4] = {0.f, 0.f, 0.f, 0.f};
+            if (s_out) {
+                const float4 u4 = rf_uniform4(key, draw_u, b, c);
+                un[0] = u4.x; un[1] = u4.y; un[2] = u4.z; un[3] = u4.w;
+            }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 p[e] = sigmoid_t<FAST>(x[e]);
-                if (s_out) s[e] = (p[e] > rf_uniform(key, draw_u, b, c + e)) ? 1.0f : 0.0f;
+                if (s_out) s[e] = (p[e] > un[e]) ? 1.0f : 0.0f;
             }
             if (logits_out) *reinterpret_cast<float4*>(logits_out + i) = make_float4(x[0], x[1], x[2], x[3]);
             if (p_out) *reinterpret_cast<float4*>(p_out + i) = make_float4(p[0], p[1], p[2], p[3]);

@@ -67,19 +67,28 @@ class RandomField:
         self.k0 = self.seed & 0xFFFFFFFF
         self.k1 = (self.seed >> 32) & 0xFFFFFFFF
 
-    def _raw(self, draw: int, rows: int, cols: int, row0: int = 0, col0: int = 0):
+    def _raw(self, draw: int, rows: int, c_lo: int, c_hi: int, row0: int = 0):
+        """Philox outputs for counters (c, row, draw, stream), c in [c_lo, c_hi] -> uint32 [rows, c_hi-c_lo+1, 4]."""
         r = (np.arange(rows, dtype=np.uint32) + np.uint32(row0))[:, None]
-        c = (np.arange(cols, dtype=np.uint32) + np.uint32(col0))[None, :]
-        return philox4x32_10(c, r, np.uint32(draw), np.uint32(self.stream), self.k0, self.k1)
+        c = np.arange(c_lo, c_hi + 1, dtype=np.uint32)[None, :]
+        return np.stack(philox4x32_10(c, r, np.uint32(draw), np.uint32(self.stream), self.k0, self.k1), axis=-1)
 
     def uniform(self, draw: int, rows: int, cols: int, row0: int = 0, col0: int = 0) -> np.ndarray:
-        x0, _, _, _ = self._raw(draw, rows, cols, row0, col0)
-        return (x0 >> np.uint32(8)).astype(np.float32) * _INV24
+        """One Philox call serves FOUR consecutive columns: column j reads word j & 3 of counter j >> 2."""
+        j = np.arange(col0, col0 + cols)
+        x = self._raw(draw, rows, int(j[0]) >> 2, int(j[-1]) >> 2, row0)
+        w = x[:, (j >> 2) - (int(j[0]) >> 2), j & 3]
+        return (w >> np.uint32(8)).astype(np.float32) * _INV24
 
     def normal(self, draw: int, rows: int, cols: int, row0: int = 0, col0: int = 0) -> np.ndarray:
-        x0, x1, _, _ = self._raw(draw, rows, cols, row0, col0)
-        u1 = ((x0 >> np.uint32(8)).astype(np.float32) + np.float32(1.0)) * _INV24
-        u2 = (x1 >> np.uint32(8)).astype(np.float32) * _INV24
+        """One Philox call serves TWO consecutive columns: column j reads words 2(j & 1), 2(j & 1) + 1 of counter
+        j >> 1 (Box-Muller, cosine branch)."""
+        j = np.arange(col0, col0 + cols)
+        x = self._raw(draw, rows, int(j[0]) >> 1, int(j[-1]) >> 1, row0)
+        idx = (j >> 1) - (int(j[0]) >> 1)
+        a, b = x[:, idx, 2 * (j & 1)], x[:, idx, 2 * (j & 1) + 1]
+        u1 = ((a >> np.uint32(8)).astype(np.float32) + np.float32(1.0)) * _INV24
+        u2 = (b >> np.uint32(8)).astype(np.float32) * _INV24
         rad = np.sqrt(np.float32(-2.0) * np.log(u1, dtype=np.float32), dtype=np.float32)
         return (rad * np.cos(_TWO_PI * u2, dtype=np.float32)).astype(np.float32)
 
