@@ -391,8 +391,10 @@ def large_batch_metric(M, dev, B=8192, V=10000, H=4096, steps=4):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    # defaults: long enough for the steady state -- with the layers pipelined the step is short enough (~115 us)
+    # that the host's first few hundred enqueues (cold caches, CPU clock ramp) would otherwise set the pace
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

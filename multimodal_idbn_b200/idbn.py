@@ -60,9 +60,12 @@ def prefetch_to_device(loader: Iterable, device, ring: int = 4):
     if prev_end is not None:
         copy_stream.wait_event(prev_end)           # the previous consumer's reads of these buffers
 
+    fences = [torch.cuda.Event() for _ in range(ring)]
+    dones = [torch.cuda.Event() for _ in range(ring)]
+
     def stage(batch, n):
         slot = n % ring
-        fence = torch.cuda.Event()
+        fence = fences[slot]
         fence.record(main)         # everything the consumer enqueued so far (it is >= 2 batches behind this one)
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(fence)
@@ -78,7 +81,7 @@ def prefetch_to_device(loader: Iterable, device, ring: int = 4):
                     bufs[(slot, pos)] = dst
                 dst.copy_(b, non_blocking=True)
                 moved.append(dst)
-            ev = torch.cuda.Event()
+            ev = dones[slot]
             ev.record(copy_stream)
         return tuple(moved), ev
 
@@ -274,15 +277,28 @@ class iDBN:
         elif loss_out is None:
             loss_t = torch.empty(n, device=dev, dtype=torch.float32)
         else:
-            if loss_out.dtype != torch.float32 or loss_out.numel() != n or not (loss_out.is_cuda or loss_out.is_pinned()):
-                raise ValueError("loss_out must hold one fp32 element per layer on the device or in pinned host memory")
+            store = loss_out.untyped_storage().data_ptr()
+            if st.get("loss_store_ok") != store:           # (is_pinned() is a driver query: once per storage)
+                if loss_out.dtype != torch.float32 or not (loss_out.is_cuda or loss_out.is_pinned()):
+                    raise ValueError("loss_out must be fp32 on the device or in pinned host memory")
+                st["loss_store_ok"] = store
+            if loss_out.numel() != n:
+                raise ValueError("loss_out must hold one element per layer")
             loss_t = loss_out
         base = loss_t.data_ptr()
+        ident = st.setdefault("ident", [None] * n)
         for l, rbm in enumerate(self.layers):
-            lr, mom = rbm._hyper(epoch)
-            st["rbms"][l] = rbm._struct(training=True)
-            st["upds"][l] = rbm._update_struct(lr, mom, B, rbm.sparsity)
-            st["rngs"][l] = rbm._next_rng()
+            # the argument structs are rebuilt only when something they describe changed (parameter storage,
+            # epoch-dependent hyper-parameters); per step only the call number of the random field moves
+            key = (rbm.W.data_ptr(), rbm.W_m.data_ptr() if getattr(rbm, "W_m", None) is not None else 0, epoch,
+                   rbm.lr, rbm.sparsity)
+            if ident[l] != key:
+                lr, mom = rbm._hyper(epoch)
+                st["rbms"][l] = rbm._struct(training=True)
+                st["upds"][l] = rbm._update_struct(lr, mom, B, rbm.sparsity)
+                ident[l] = (rbm.W.data_ptr(), rbm.W_m.data_ptr(), epoch, rbm.lr, rbm.sparsity)
+            r = rbm._next_rng()
+            st["rngs"][l] = r
             st["loss"][l] = base + 4 * l
         first = self.layers[0]
         cached = first.__dict__.pop("_pos_cache", None)
