@@ -406,7 +406,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         if args.steps > 64:
-            args.steps = 64            # bounded sample: ~0.2 s per CPU step
+            args.steps = 64            # bounded sample: ~0.13 s per CPU step
+        args.warmup = min(args.warmup, 2)
         run_reference(args)
     else:
         run_ours(args)
