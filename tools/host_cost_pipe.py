@@ -26,3 +26,14 @@ for pipe in (False, True):
     for i in range(300): m.train_step(x[i % 8], 0, 1, next_v=x[(i + 1) % 8])
     m.sync(); e1.record(); torch.cuda.synchronize()
     print(f"pipeline={pipe}: host enqueue {best:.1f} us/step; steady state {e0.elapsed_time(e1) / 300 * 1e3:.1f} us/step")
+import cProfile, pstats
+for pipe in (False, True):
+    m = M.iDBN([10000, 1500, 500], P, None, None, dev)
+    m.pipeline_layers = pipe
+    for i in range(60): m.train_step(x[i % 8], 0, 1, next_v=x[(i + 1) % 8])
+    torch.cuda.synchronize()
+    pr = cProfile.Profile(); pr.enable()
+    for i in range(40): m.train_step(x[i % 8], 0, 1, next_v=x[(i + 1) % 8])
+    pr.disable(); m.sync(); torch.cuda.synchronize()
+    print("pipeline", pipe)
+    pstats.Stats(pr).sort_stats("tottime").print_stats(6)
