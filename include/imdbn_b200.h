@@ -153,12 +153,13 @@ int imdbn_idbn_train_step(imdbn_ctx* ctx0, imdbn_ctx* ctx1, int n_layers, const 
                           imdbn_stream caller_stream /* nullable: stream the inputs were produced on, if not stream0 */,
                           int early_launch /* 0: layer 0 without programmatic dependent launch */);
 
-/* Two streams whose kernels run on DISJOINT sets of SMs (CUDA green contexts, created once per device): the small
+/* (No reference counterpart: the reference runs the layers of idbn.py:199-204 back to back on one stream.)
+ * Two streams whose kernels run on DISJOINT sets of SMs (CUDA green contexts, created once per device): the small
  * partition has >= small_sms SMs (multiples of 8), the big one the rest.  Used to train the upper layers of an
  * iDBN next to the bottom layer without either side's early-launched grids squatting on the other's SMs. */
 int imdbn_sm_partition(int device, int small_sms, void** stream_big, void** stream_small, int* n_big, int* n_small);
 
-/* The same statistics without the update, for batches sharded over ranks: writes the local sums
+/* The same statistics without the update (rbm.py:199-209, 216, 223, 226), for batches sharded over ranks: writes the local sums
  *   stats_out = [ dS (V*H) | dh (H) | dv (V) | pos_h column sum (H) | squared error (1) ]
  * which the host all-reduces (NCCL) and hands to imdbn_apply_update on every rank. */
 int imdbn_cd_stats(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* data, int B, int k,
