@@ -2,6 +2,7 @@
 // Host-side sequencing of the reference's RBM methods (imdbn/models/rbm.py); every function only
 // enqueues kernels on the caller's stream.
 #include <algorithm>
+#include <ctime>
 #include <vector>
 
 #include "common.cuh"
@@ -930,6 +931,11 @@ int imdbn_idbn_train_step(imdbn_ctx* ctx0, imdbn_ctx* ctx1, int n_layers, const 
     IMDBN_ARG(ctx0, ctx0 && n_layers >= 1 && rbms && upds && rngs && data && fwd_out && loss_out && B > 0);
     IMDBN_ARG(ctx0, buffer_set == 0 || buffer_set == 1);
     cudaStream_t s0 = (cudaStream_t)stream0, s1 = (cudaStream_t)stream1, sc = (cudaStream_t)caller_stream;
+    static const bool host_trace = getenv("IMDBN_HOST_TRACE") != nullptr;
+    static double acc_t[4] = {0, 0, 0, 0};
+    static long acc_n = 0;
+    auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
+    const double t_begin = host_trace ? now() : 0;
     const bool foreign = caller_stream != nullptr && sc != s0;      // layer 0 runs on a stream other than the caller's
     if (foreign) {
         if (!ctx0->ev_in) {
@@ -957,9 +963,11 @@ int imdbn_idbn_train_step(imdbn_ctx* ctx0, imdbn_ctx* ctx1, int n_layers, const 
     // Without an SM partition an early-launched dependent grid parks its CTAs on the SMs that were meant for the
     // other stream: the caller then asks for plain stream-ordered launches of layer 0.
     if (piped && !early_launch) pdl_early() = false;
+    const double t_l0 = host_trace ? now() : 0;
     int rc = cd_core(ctx0, &rbms[0], data, B, k, &upds[0], &rngs[0], loss_out[0], nullptr, s0, &t0);
     pdl_early() = true;
     if (rc) return rc;
+    const double t_l0_end = host_trace ? now() : 0;
     if (foreign) {                                                    // the caller's stream sees layer 0's results
         IMDBN_CUDA(ctx0, cudaEventRecord(ctx0->ev_out, s0));
         IMDBN_CUDA(ctx0, cudaStreamWaitEvent(sc, ctx0->ev_out, 0));
@@ -981,6 +989,15 @@ int imdbn_idbn_train_step(imdbn_ctx* ctx0, imdbn_ctx* ctx1, int n_layers, const 
         }
     }
     if (piped) IMDBN_CUDA(ctx0, cudaEventRecord(ctx0->ev_done[par], s1));
+    if (host_trace) {
+        const double t_end = now();
+        acc_t[0] += t_l0 - t_begin; acc_t[1] += t_l0_end - t_l0; acc_t[2] += t_end - t_l0_end; acc_t[3] += t_end - t_begin;
+        if (++acc_n % 500 == 0) {
+            fprintf(stderr, "imdbn_idbn_train_step host us/call: entry+events %.1f, layer 0 %.1f, upper layers+events %.1f, total %.1f (piped=%d)\n",
+                    acc_t[0] / 500, acc_t[1] / 500, acc_t[2] / 500, acc_t[3] / 500, (int)piped);
+            acc_t[0] = acc_t[1] = acc_t[2] = acc_t[3] = 0;
+        }
+    }
     return 0;
 }
 

@@ -163,3 +163,44 @@ def test_block_mask_hint_gives_identical_chains():
         assert torch.equal(outs[2][:, Dz:], y)
     finally:
         M.set_precision("fp32")
+
+
+def test_c2_full_size_pipelined_matches_unpipelined(tmp_path, monkeypatch):
+    """BASELINE config C2 at full size (iDBN [10000,1500,500], batch 64, tf32): the layer-pipelined step on SM
+    partitions and the plain step give the same parameters up to the split-K summation order, and the losses
+    written into pinned host memory equal the returned device losses."""
+    monkeypatch.chdir(tmp_path)
+    import multimodal_idbn_b200 as M
+    M.set_precision("tf32")
+    try:
+        p = dict(LEARNING_RATE=0.1, WEIGHT_PENALTY=1e-4, INIT_MOMENTUM=0.5, FINAL_MOMENTUM=0.95, LEARNING_RATE_DYNAMIC=True)
+        xs = [(torch.rand(64, 10000, generator=torch.Generator().manual_seed(s)) < 0.1).float().to(DEV) for s in range(5)]
+        runs = []
+        for piped in (False, True):
+            torch.manual_seed(0)
+            m = M.iDBN([10000, 1500, 500], dict(p), None, None, torch.device(DEV))
+            for i, l in enumerate(m.layers):
+                l.set_rng(40 + i, 0)
+            m.pipeline_layers = piped
+            host = torch.full((4, 2), float("nan")).pin_memory()
+            dev_losses = []
+            for t in range(4):
+                if t % 2 == 0:
+                    m.train_step(xs[t], 0, 1, next_v=xs[t + 1], loss_out=host[t])
+                else:
+                    step = m.train_step(xs[t], 0, 1, next_v=xs[t + 1])
+                    m.sync()
+                    dev_losses.append(torch.stack(step).cpu())
+            m.sync(); torch.cuda.synchronize()
+            assert torch.isfinite(host[0]).all() and torch.isfinite(host[2]).all()
+            runs.append((host[[0, 2]].clone(), torch.stack(dev_losses), [l.W.detach().cpu() for l in m.layers],
+                         m.represent(xs[0]).cpu()))
+        a, b = runs
+        torch.testing.assert_close(b[0], a[0], rtol=2e-3, atol=1e-5)
+        torch.testing.assert_close(b[1], a[1], rtol=2e-3, atol=1e-5)
+        for wa, wb in zip(a[2], b[2]):
+            # a hidden unit within rounding of its threshold may flip with the summation order: almost all entries tight
+            assert float(((wa - wb).abs() > 1e-4).float().mean()) < 5e-3
+        assert float((a[3] - b[3]).abs().mean()) < 2e-3
+    finally:
+        M.set_precision("fp32")
