@@ -194,6 +194,10 @@ _contexts: Dict[Tuple[int, int], Context] = {}
 _precision = PREC_FP32
 
 
+def current_precision() -> int:
+    return _precision
+
+
 def set_precision(name: str):
     """'fp32' (parity mode, FFMA) or 'tf32' (tcgen05 tensor-core passes)."""
     global _precision

@@ -25,6 +25,8 @@ from .rbm import RBM
 
 def _flat(x: torch.Tensor, device) -> torch.Tensor:
     """``img.to(device).view(B, -1).float()`` (idbn.py:200,319,336)."""
+    if x.dim() == 2 and x.dtype is torch.float32 and x.device == device:      # already in place (the hot loop)
+        return x
     x = x.to(device, non_blocking=True)
     return x.reshape(x.size(0), -1).float()
 
@@ -229,14 +231,20 @@ class iDBN:
         dev = v.device
         n = len(self.layers)
         B = v.shape[0]
+        if not v.is_contiguous():
+            v = v.contiguous()
         nxt = _flat(next_v, dev) if next_v is not None else None
+        if nxt is not None and not nxt.is_contiguous():
+            nxt = nxt.contiguous()
         Bn = nxt.shape[0] if nxt is not None else 0
-        piped = bool(getattr(self, "pipeline_layers", False)) and n > 1
-        reserve = int(getattr(self, "pipeline_reserve_sms", 16)) if piped else 0
-        ctx_c, s_caller = L.context_for(v)
-        st = self.__dict__.get("_fused")
-        key = (B, Bn, dev, s_caller, piped, reserve, tuple(r.num_hidden for r in self.layers))
+        d = self.__dict__
+        piped = bool(d.get("pipeline_layers", False)) and n > 1
+        reserve = int(d.get("pipeline_reserve_sms", 16)) if piped else 0
+        s_caller = torch.cuda.current_stream(dev).cuda_stream
+        st = d.get("_fused")
+        key = (B, Bn, dev, s_caller, piped, reserve, n, id(self.layers[-1]))
         if st is None or st["key"] != key:
+            ctx_c, s_caller = L.context_for(v)
             rings = [[torch.empty(B + (Bn if l == 0 else 0), r.num_hidden, device=dev, dtype=torch.float32)
                       for l, r in enumerate(self.layers)] for _ in range(2)]
             st = dict(key=key, rings=rings, parity=0, ctx0=ctx_c, s0=s_caller, ctx1=None, s1=0, early=1, streams=[],
@@ -286,20 +294,28 @@ class iDBN:
                 raise ValueError("loss_out must hold one element per layer")
             loss_t = loss_out
         base = loss_t.data_ptr()
+        st["ctx0"].set_precision(L.current_precision())
         ident = st.setdefault("ident", [None] * n)
+        rngs, loss_ptrs = st["rngs"], st["loss"]
         for l, rbm in enumerate(self.layers):
             # the argument structs are rebuilt only when something they describe changed (parameter storage,
             # epoch-dependent hyper-parameters); per step only the call number of the random field moves
-            key = (rbm.W.data_ptr(), rbm.W_m.data_ptr() if getattr(rbm, "W_m", None) is not None else 0, epoch,
-                   rbm.lr, rbm.sparsity)
+            rd = rbm.__dict__
+            wm = rd.get("W_m")
+            key = (rbm._parameters["W"].data_ptr(), wm.data_ptr() if wm is not None else 0, epoch, rd["lr"],
+                   rd["sparsity"])
             if ident[l] != key:
                 lr, mom = rbm._hyper(epoch)
                 st["rbms"][l] = rbm._struct(training=True)
                 st["upds"][l] = rbm._update_struct(lr, mom, B, rbm.sparsity)
                 ident[l] = (rbm.W.data_ptr(), rbm.W_m.data_ptr(), epoch, rbm.lr, rbm.sparsity)
-            r = rbm._next_rng()
-            st["rngs"][l] = r
-            st["loss"][l] = base + 4 * l
+            if "_rng_seed" not in rd:                    # object un-pickled from a reference checkpoint
+                rngs[l] = rbm._next_rng()
+            else:
+                r = rngs[l]
+                r.seed, r.stream, r.row0 = rd["_rng_seed"], rd["_rng_stream"] & 0xFFFFFFFF, 0
+                rd["_rng_stream"] += 1
+            loss_ptrs[l] = base + 4 * l
         first = self.layers[0]
         cached = first.__dict__.pop("_pos_cache", None)
         pos_in = cached[1] if cached is not None and cached[0] == first._pos_key(v) else None
@@ -309,11 +325,12 @@ class iDBN:
             L.ptr(v), B, int(self.cd_k), L.ptr(pos_in), L.ptr(nxt), Bn, st["fwd"][par], st["loss"], par, st["s0"],
             st["s1"], s_caller, st["early"]), "imdbn_idbn_train_step")
         for rbm in self.layers:
-            rbm._n_updates = getattr(rbm, "_n_updates", 0) + 1
-            rbm.__dict__.pop("_pos_cache", None)
+            rd = rbm.__dict__
+            rd["_n_updates"] = rd.get("_n_updates", 0) + 1
+            rd.pop("_pos_cache", None)
         if nxt is not None:
-            first._pos_cache = (first._pos_key(nxt), st["rings"][par][0][B:])
-        return [loss_t[l] for l in range(n)]
+            first.__dict__["_pos_cache"] = (first._pos_key(nxt), st["rings"][par][0][B:])
+        return list(loss_t.unbind(0))
 
     def sync(self) -> None:
         """Make the current stream wait for the upper layers' side stream (call before reading losses or
