@@ -278,6 +278,13 @@ static inline uint64_t l2_policy_env(const char* name, uint64_t dflt) {
     if (!strcmp(e, "last")) return L2_EVICT_LAST;
     return dflt;
 }
+// Weights of a small layer (<= 16 MB for W and W_m together) are re-read by every pass of every step: ask L2 to keep
+// them (evict_last) so that they survive the 240 MB a large layer streams through the cache when both train
+// concurrently; the big layer's streams can be marked evict_first.  IMDBN_L2_SMALL / IMDBN_L2_BIG override.
+static inline uint64_t l2_policy_for(const imdbn_rbm* r) {
+    const bool small = (size_t)r->V * r->H * 8 <= ((size_t)16 << 20);
+    return small ? l2_policy_env("IMDBN_L2_SMALL", L2_EVICT_NORMAL) : l2_policy_env("IMDBN_L2_BIG", L2_EVICT_NORMAL);
+}
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static inline int npad_of(int B) { return std::max(16, (B + 15) / 16 * 16); }
 static inline uint32_t pow2_cols(int n) { uint32_t c = 32; while ((int)c < n) c <<= 1; return c; }
@@ -346,7 +353,7 @@ static int stream_pass(imdbn_ctx* ctx, const imdbn_rbm* r, const float* act, int
     a.total_iters = ((M_total + TS_BM - 1) / TS_BM) * a.sk.k_iters;
     a.part = part;
     a.tmem_cols = pow2_cols(2 * a.Npad);
-    a.w_policy = l2_policy_env("IMDBN_L2_W", L2_EVICT_NORMAL);
+    a.w_policy = l2_policy_for(r);
     a.stages = std::max(2, std::min(TS_STAGES, (200 * 1024) / ts_stage_bytes(a.Npad)));
     const int G = tc_plan_ctas(a.sk, M_total);
     // W is [V, H] row-major: inner = H.  up: boxes [64 k-rows x 32 h]; down: boxes [128 v-rows x 32 h]
@@ -419,8 +426,8 @@ int tc_gemm_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* vp, const flo
     { static const int dbg_env = getenv("IMDBN_DEBUG_STATS") ? atoi(getenv("IMDBN_DEBUG_STATS")) : 0; a.dbg = dbg_env; }
     a.late_wait = ctx->stats_after_colstats ? 1 : 0;
     ctx->stats_after_colstats = false;
-    a.w_policy = l2_policy_env("IMDBN_L2_W", L2_EVICT_NORMAL);
-    a.wm_policy = l2_policy_env("IMDBN_L2_WM", L2_EVICT_NORMAL);
+    a.w_policy = l2_policy_for(r);
+    a.wm_policy = l2_policy_for(r);
     const CUtensorMap* tVP = get_map(ctx, vp, r->V, B, ST_KC, true);
     const CUtensorMap* tVN = get_map(ctx, vn, r->V, B, ST_KC, true);
     const CUtensorMap* tHP = get_map(ctx, hp, r->H, B, ST_KC, true);
