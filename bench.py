@@ -393,8 +393,10 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     # defaults: long enough for the steady state -- with the layers pipelined the step is short enough (~115 us)
     # that the host's first few hundred enqueues (cold caches, CPU clock ramp) would otherwise set the pace
+    # (the warm-up also has to outlast the start-up regime in which the upper layer still lags behind the bottom one
+    # and the bottom layer runs at its own, faster, pace: ~500 steps, tools/step_trend.py)
     ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=600)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
