@@ -5,6 +5,10 @@ both fed the same Philox random field.
 Tolerances (north_star): sampled binary / one-hot states bit-exact except units whose probability is
 within 1e-6 of the uniform they are compared with; activations / weights within 2e-5 absolute-or-
 relative in fp32 parity mode (different summation order than MKL, nothing else)."""
+import os
+import subprocess
+import sys
+
 import numpy as np
 import pytest
 import torch
@@ -587,3 +591,16 @@ def test_train_step_variants_are_identical(M, tmp_path, monkeypatch, prec):
             torch.testing.assert_close(b, a, **tol)
     finally:
         M.set_precision("fp32")
+
+
+def test_pipelining_without_sm_partition_fallback():
+    """IMDBN_NO_PARTITION=1 (what profiling runs use): the pipelined step falls back to an ordinary side stream
+    with early dependent launch switched off for layer 0, and must give the same results."""
+    if os.environ.get("IMDBN_NO_PARTITION"):
+        pytest.skip("already running without SM partitions")
+    env = dict(os.environ, IMDBN_NO_PARTITION="1")
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k",
+                          "train_step_variants"], env=env, capture_output=True, text=True, timeout=600,
+                         cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-1000:]
+    assert "2 passed" in out.stdout
