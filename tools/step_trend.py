@@ -16,11 +16,16 @@ for i in range(NB): m.train_step(x[i % NB], 0, 1, next_v=x[(i + 1) % NB])
 m.sync(); torch.cuda.synchronize()
 NC = int(os.environ.get('CHUNKS', 12))
 evs = [torch.cuda.Event(enable_timing=True) for _ in range(NC + 1)]
+import time
 k = 0
+host = []
 evs[0].record()
 for c in range(NC):
+    t0 = time.perf_counter()
     for i in range(100):
         m.train_step(x[k % NB], 0, 1, next_v=x[(k + 1) % NB]); k += 1
+    host.append(round((time.perf_counter() - t0) * 1e4, 1))
     evs[c + 1].record()
 m.sync(); torch.cuda.synchronize()
+print("host us/step per chunk:       ", host)
 print("us/step per 100-step chunk:", [round(evs[c].elapsed_time(evs[c + 1]) * 10, 1) for c in range(NC)])
