@@ -302,7 +302,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
         "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32" if args.precision == "fp32" else "tf32", "data": "synthetic",
+        "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x2": "tf32x2 (split tf32 operands, fp32 accumulate: fp32-faithful)"}[args.precision], "data": "synthetic",
         "config": {"workload": "C2 iDBN [10000,1500,500] CD-1 batch 64 per GPU (idbn.py:199-204)",
                    "global_batch": BATCH * world,
                    "parallelism": dp_desc,
@@ -398,7 +398,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=600)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"])
+    ap.add_argument("--precision", default="tf32x2", choices=["fp32", "tf32", "tf32x2"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pipeline-reserve", type=int, default=16,
                     help="SMs left to the upper layers, which then run on a side stream concurrently with the next "

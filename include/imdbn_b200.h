@@ -69,7 +69,9 @@ typedef struct {
 /* Precision of the GEMM-shaped passes. */
 enum {
     IMDBN_PREC_FP32 = 0, /* fp32 FFMA accumulation: parity mode (samples bit-exact up to 1e-6) */
-    IMDBN_PREC_TF32 = 1  /* tcgen05 kind::tf32, fp32 accumulate in TMEM (<=1e-3 relative) */
+    IMDBN_PREC_TF32 = 1, /* tcgen05 kind::tf32, fp32 accumulate in TMEM (<=1e-3 relative) */
+    IMDBN_PREC_TF32X2 = 2 /* exact mode on the tensor cores: every operand enters as hi + lo tf32 terms (22+ significand
+                           * bits), fp32 accumulate in TMEM, IEEE finishes: samples bit-exact up to 1e-6 like FP32 */
 };
 
 /* ---- context ------------------------------------------------------------------------------ */

@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libimdbn_b200.so")
 
 MAX_GROUPS = 4
-PREC_FP32, PREC_TF32 = 0, 1
+PREC_FP32, PREC_TF32, PREC_TF32X2 = 0, 1, 2
 CHAIN_NOISY_MF, CHAIN_COND_GIBBS = 0, 1
 KERNEL_UP, KERNEL_DOWN, KERNEL_STATS, KERNEL_CHAIN = 0, 1, 2, 3
 
@@ -199,16 +199,17 @@ def current_precision() -> int:
 
 
 def set_precision(name: str):
-    """'fp32' (parity mode, FFMA) or 'tf32' (tcgen05 tensor-core passes)."""
+    """'fp32' (parity mode, FFMA), 'tf32' (tcgen05 tensor-core passes, 1e-3) or 'tf32x2' (exact mode on the tensor
+    cores: hi + lo tf32 terms of every operand, same parity bars as 'fp32')."""
     global _precision
-    table = {"fp32": PREC_FP32, "tf32": PREC_TF32}
+    table = {"fp32": PREC_FP32, "tf32": PREC_TF32, "tf32x2": PREC_TF32X2}
     if name not in table:
         raise ValueError(f"precision must be one of {sorted(table)}")
     _precision = table[name]
 
 
 def get_precision() -> str:
-    return {PREC_FP32: "fp32", PREC_TF32: "tf32"}[_precision]
+    return {PREC_FP32: "fp32", PREC_TF32: "tf32", PREC_TF32X2: "tf32x2"}[_precision]
 
 
 def context_for(t: torch.Tensor) -> Tuple[Context, int]:

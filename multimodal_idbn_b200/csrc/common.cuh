@@ -39,7 +39,13 @@ struct imdbn_ctx {
     // transposed-weight cache for the chain kernels is rebuilt on every call (W changes between
     // updates); it lives in the arena like everything else.
     void* tc = nullptr;  // tensor-core path state (tc_gemm.cu), opaque here
+    bool w_stable = false;               // the next tensor-core pass may read W before its grid-dependency wait: no kernel
+                                         // still in flight writes W (set by cd_core around the passes of one CD-k update)
+    bool act_exact = false;              // the activations of the next tensor-core pass are sampled states (0 / 1): exactly
+                                         // representable in tf32, the exact mode needs no remainder tile for them
     bool stats_after_colstats = false;   // next tc statistics kernel directly follows k_colstats (see tc_stats.cuh)
+    uint32_t* pack_flags = nullptr;      // device: [0] = generation of the last statistics call whose v operand was inexact in tf32
+    uint32_t pack_gen = 0;
     unsigned int* ticket = nullptr;   // device counter of the last-block reductions (self-resetting)
     // imdbn_idbn_train_step with a second context: cross-stream events (created lazily)
     cudaEvent_t ev_ready = nullptr, ev_in = nullptr, ev_out = nullptr;
@@ -53,6 +59,10 @@ namespace imdbn {
 inline int tc_sms(const imdbn_ctx* ctx) {
     return ctx->tc_sms > 0 && ctx->tc_sms < ctx->num_sms ? ctx->tc_sms : ctx->num_sms;
 }
+
+// tensor-core passes (tf32 or the split exact mode) / reduced-accuracy intrinsics in the finishes (tf32 only)
+inline bool uses_tc(const imdbn_ctx* ctx) { return ctx->precision != IMDBN_PREC_FP32; }
+inline bool fast_math(const imdbn_ctx* ctx) { return ctx->precision == IMDBN_PREC_TF32; }
 
 inline int fail(imdbn_ctx* ctx, int code, const char* what) {
     if (ctx) {

@@ -43,7 +43,7 @@ struct PassPlan {
 PassPlan plan_pass(const imdbn_ctx* ctx, const imdbn_rbm* r, int B, bool up) {
     const int M = B, N = up ? r->H : r->V, K = up ? r->V : r->H;
     PassPlan p{};
-    const bool tc = ctx->precision == IMDBN_PREC_TF32 &&
+    const bool tc = uses_tc(ctx) &&
                     (up ? tc_up_supported(ctx, r, B) : tc_down_supported(ctx, r, B));
     if (tc) {
         p.sk = tc_plan(ctx, N, K);
@@ -98,7 +98,7 @@ int gemm_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* vp, const float*
                const float* vn, const float* hn, int B, float* dS_out, const imdbn_update* upd,
                cudaStream_t st) {
     ProfScope prof(ctx, IMDBN_KERNEL_STATS, r->V, r->H, st);
-    if (ctx->precision == IMDBN_PREC_TF32 && tc_stats_supported(ctx, r, B))
+    if (uses_tc(ctx) && tc_stats_supported(ctx, r, B))
         return tc_gemm_stats(ctx, r, vp, hp, vn, hn, B, dS_out, upd, st);
     GemmArgs g{};
     g.A = vp; g.sAm = 1; g.sAk = r->V;
@@ -133,7 +133,7 @@ int up_pass(imdbn_ctx* ctx, const imdbn_rbm* r, const float* v, int B, float T, 
     if (rc) return rc;
     if (vec_ok(B, r->H, r->hb, p_out, s_out, nullptr)) {
         const size_t quads = (size_t)B * (r->H / 4);
-        if (ctx->precision == IMDBN_PREC_TF32)
+        if (fast_math(ctx))
             IMDBN_CUDA(ctx, launch_pdl(k_finish_up4<true>, dim3(vec_blocks(quads, ctx->num_sms)), dim3(256), 0, st,
                                        part, pl.splits, pl.sk, B, r->H, r->hb, fmaxf(1e-6f, T), 0.0f, p_out, s_out,
                                        key, draw_u, 0u));
@@ -160,7 +160,7 @@ int down_pass(imdbn_ctx* ctx, const imdbn_rbm* r, const float* h, int B, float T
     if (vec_ok(B, r->V, r->vb, p_out, s_out, lg)) {
         const size_t quads = (size_t)B * (r->V / 4);
         ChainPost4 cp{};
-        if (ctx->precision == IMDBN_PREC_TF32)
+        if (fast_math(ctx))
             IMDBN_CUDA(ctx, launch_pdl(k_finish_down4<true>, dim3(vec_blocks(quads, ctx->num_sms)), dim3(256), 0, st,
                                        part, pl.splits, pl.sk, B, r->V, r->vb, fmaxf(1e-6f, T), 0.0f, p_out, lg, s_out,
                                        key, draw_u, 0u, cp));
@@ -253,7 +253,7 @@ bool chain_is_label_only(const imdbn_rbm* r, const imdbn_chain* ch, const float*
 // Large mean-field batches in tf32 mode run the chain step by step on the tensor-core passes
 // (chain_stepped.cuh); everything else uses the persistent kernel.
 bool chain_is_stepped(const imdbn_ctx* ctx, const imdbn_rbm* r, const imdbn_chain* ch, int B) {
-    return ctx->precision == IMDBN_PREC_TF32 && B >= 512 && !ch->sample_h && !ch->sample_v &&
+    return uses_tc(ctx) && B >= 512 && !ch->sample_h && !ch->sample_v &&
            tc_up_supported(ctx, r, B) && tc_down_supported(ctx, r, B);
 }
 
@@ -296,8 +296,11 @@ int run_chain_stepped(imdbn_ctx* ctx, const imdbn_rbm* r, const imdbn_chain* ch,
         const uint32_t d_h = ch->draw0 + 1 + (noisy ? 2 : 3) * t, d_v = d_h + 1;
         int rc = gemm_up(ctx, r, v, B, pu, part, st);                                 // rbm.py:344 / 394
         if (rc) return rc;
-        if (vec)
+        if (vec && fast_math(ctx))
             IMDBN_CUDA(ctx, launch_pdl(k_finish_up4<true>, dim3(vec_blocks((size_t)B * (H / 4), ctx->num_sms)), dim3(256),
+                                       0, st, part, pu.splits, pu.sk, B, H, r->hb, T, sig, h, (float*)nullptr, key, 0u, d_h));
+        else if (vec)
+            IMDBN_CUDA(ctx, launch_pdl(k_finish_up4<false>, dim3(vec_blocks((size_t)B * (H / 4), ctx->num_sms)), dim3(256),
                                        0, st, part, pu.splits, pu.sk, B, H, r->hb, T, sig, h, (float*)nullptr, key, 0u, d_h));
         else
             IMDBN_CUDA(ctx, launch_pdl(k_chain_up_finish, gh, dim3(256), 0, st, part, pu.splits, pu.sk, B, H, r->hb,
@@ -315,7 +318,7 @@ int run_chain_stepped(imdbn_ctx* ctx, const imdbn_rbm* r, const imdbn_chain* ch,
         // block-mask promise (TXT->IMG): honoured on the vector path when no softmax group straddles the boundary
         po.clamp_from = -1;
         bool groups_clamped = false;
-        if (vec && ch->clamp_suffix >= 0 && ch->clamp_suffix < V && ch->clamp_suffix % 4 == 0) {
+        if (vec && ch->clamp_suffix > 0 && ch->clamp_suffix < V && ch->clamp_suffix % 4 == 0) {
             int n_clamped = 0, n_free = 0, n_straddle = 0;
             for (int g = 0; g < gr.n; ++g) {
                 if (gr.s[g] >= ch->clamp_suffix) ++n_clamped;
@@ -331,9 +334,14 @@ int run_chain_stepped(imdbn_ctx* ctx, const imdbn_rbm* r, const imdbn_chain* ch,
         }
         if (vec) {
             ChainPost4 cp{}; cp.enabled = 1; cp.po = po;
-            IMDBN_CUDA(ctx, launch_pdl(k_finish_down4<true>, dim3(vec_blocks((size_t)B * (V / 4), ctx->num_sms)), dim3(256),
-                                       0, st, part, pd.splits, pd.sk, B, V, r->vb, T, sig, v, lg, (float*)nullptr, key, 0u,
-                                       d_v, cp));
+            if (fast_math(ctx))
+                IMDBN_CUDA(ctx, launch_pdl(k_finish_down4<true>, dim3(vec_blocks((size_t)B * (V / 4), ctx->num_sms)), dim3(256),
+                                           0, st, part, pd.splits, pd.sk, B, V, r->vb, T, sig, v, lg, (float*)nullptr, key, 0u,
+                                           d_v, cp));
+            else
+                IMDBN_CUDA(ctx, launch_pdl(k_finish_down4<false>, dim3(vec_blocks((size_t)B * (V / 4), ctx->num_sms)), dim3(256),
+                                           0, st, part, pd.splits, pd.sk, B, V, r->vb, T, sig, v, lg, (float*)nullptr, key, 0u,
+                                           d_v, cp));
         } else {
             IMDBN_CUDA(ctx, launch_pdl(k_chain_down_finish, gv, dim3(256), 0, st, part, pd.splits, pd.sk, B, V, r->vb,
                                        T, sig, key, d_v, po, lg, v));
@@ -382,7 +390,7 @@ int run_chain_label_only(imdbn_ctx* ctx, const imdbn_rbm* r, const imdbn_chain* 
     const int blocks = std::max(1, std::min((B + per_cta - 1) / per_cta, ctx->num_sms * 2));
     {
         ProfScope prof(ctx, IMDBN_KERNEL_CHAIN, V, H, st);
-        if (ctx->precision == IMDBN_PREC_TF32) k_label_gibbs<true><<<blocks, LG_WARPS * 32, smem, st>>>(a);
+        if (fast_math(ctx)) k_label_gibbs<true><<<blocks, LG_WARPS * 32, smem, st>>>(a);
         else k_label_gibbs<false><<<blocks, LG_WARPS * 32, smem, st>>>(a);
         IMDBN_CHECK_LAUNCH(ctx, "k_label_gibbs");
     }
@@ -590,14 +598,22 @@ int cd_core(imdbn_ctx* ctx, const imdbn_rbm* r, const float* data, int B, int k,
         rc = up_pass(ctx, r, data, B, 1.0f, pos_h, h_s, key, 0, pu, part, st);      // rbm.py:199,203
         if (rc) return rc;
     }
+    // From here to the statistics kernel nothing writes W, and the kernel above is either a plain launch or a pass
+    // that triggers only after its own wait: the passes of the CD loop may stream W before their predecessor is done.
+    static const bool no_prefetch = getenv("IMDBN_NO_W_PREFETCH") != nullptr;
+    ctx->w_stable = !no_prefetch;
+    ctx->act_exact = true;                 // h_s and v_s are sampled states
     for (int s = 0; s < k; ++s) {
         rc = down_pass(ctx, r, h_s, B, 1.0f, v_prob, nullptr, v_s, lg_tmp, key, 1 + 3 * s,
                        2 + 3 * s, pd, part, st);                                        // :205-206
-        if (rc) return rc;
+        if (rc) break;
         rc = up_pass(ctx, r, v_s, B, 1.0f, h_prob, (s + 1 < k) ? h_s : nullptr, key, 3 + 3 * s, pu,
                      part, st);                                                         // :207-208
-        if (rc) return rc;
+        if (rc) break;
     }
+    ctx->w_stable = false;
+    ctx->act_exact = false;
+    if (rc) return rc;
     // The bias / loss kernel and the weight-statistics kernel share only read-only inputs (the biases are
     // not read by the statistics GEMM, W is not read by the column statistics), so their order does not
     // matter; the column statistics go first and the tensor-core statistics kernel overlaps them.
@@ -642,6 +658,7 @@ int clamped_core(imdbn_ctx* ctx, const imdbn_rbm* r, const float* v_known, const
     const int nb_sq = colstat_blocks(r);
     imdbn_chain chq{};                       // only what the workspace sizing looks at
     chq.n_steps = n;
+    chq.clamp_prefix = chq.clamp_suffix = -1;
     chq.sample_h = cfg->use_noisy_init ? 0 : cfg->sample_h;
     chq.sample_v = cfg->use_noisy_init ? 0 : cfg->sample_v;
     size_t bytes = pad256(std::max(pu.part_floats, pd.part_floats)) + 3 * pad256(nBH) +
@@ -667,6 +684,8 @@ int clamped_core(imdbn_ctx* ctx, const imdbn_rbm* r, const float* v_known, const
     imdbn_chain ch{};
     std::vector<float> T, S, E;
     ch.v_known = v_known; ch.known_mask = km; ch.n_steps = n; ch.draw0 = 0;
+    ch.clamp_prefix = ch.clamp_suffix = -1;      // arbitrary mask: no block-mask promise (a zero-initialised 0 would
+                                                 // read as "every column clamped" in the stepped chain)
     uint32_t base;
     if (cfg->use_noisy_init) {
         // T0=3, T1=1, sigma0=.9, sharpen_last=2, T_cold_plus=.9 (rbm.py:444-448, schedule :229-234,338-341)
@@ -779,6 +798,7 @@ void imdbn_ctx_destroy(imdbn_ctx* ctx) {
     tc_destroy(ctx);
     prof_clear(ctx);
     if (ctx->ticket) cudaFree(ctx->ticket);
+    if (ctx->pack_flags) cudaFree(ctx->pack_flags);
     if (ctx->ev_ready) cudaEventDestroy(ctx->ev_ready);
     if (ctx->ev_in) cudaEventDestroy(ctx->ev_in);
     if (ctx->ev_out) cudaEventDestroy(ctx->ev_out);
@@ -801,7 +821,7 @@ int imdbn_set_sm_limit(imdbn_ctx* ctx, int n_sms) {
 }
 
 int imdbn_set_precision(imdbn_ctx* ctx, int prec) {
-    IMDBN_ARG(ctx, ctx && (prec == IMDBN_PREC_FP32 || prec == IMDBN_PREC_TF32));
+    IMDBN_ARG(ctx, ctx && (prec == IMDBN_PREC_FP32 || prec == IMDBN_PREC_TF32 || prec == IMDBN_PREC_TF32X2));
     ctx->precision = prec;
     return 0;
 }
@@ -1147,6 +1167,8 @@ int imdbn_assoc_stats(imdbn_ctx* ctx, const imdbn_rbm* rbm, const float* vp, con
     int rc = check_rbm(ctx, rbm, false);
     if (rc) return rc;
     IMDBN_ARG(ctx, vp && hp && vn && hn && dS_out && B > 0);
+    rc = arena_begin(ctx, tc_ws_bytes(ctx, rbm, B), (cudaStream_t)stream);
+    if (rc) return rc;
     return gemm_stats(ctx, rbm, vp, hp, vn, hn, B, dS_out, nullptr, (cudaStream_t)stream);
 }
 

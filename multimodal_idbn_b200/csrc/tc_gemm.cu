@@ -99,11 +99,22 @@ static const CUtensorMap* get_map(imdbn_ctx* ctx, const float* ptr, int inner, i
 // ------------------------------------------------------------------------------------------------
 // weight-streaming pass kernel
 // ------------------------------------------------------------------------------------------------
+// SPLIT = the exact mode (IMDBN_PREC_TF32X2): tcgen05 kind::tf32 reads only the top 19 bits of an fp32 word, so
+// every operand x is used as x = hi + lo with hi = the truncated word the hardware sees and lo = x - hi (exact in
+// fp32, <= 13 significant bits, of which the hardware keeps 11: 22+ bits of x in total).  Four converter warps
+// turn each W tile that TMA delivered into its lo tile in a second shared-memory buffer (element-wise, so the
+// swizzled layout is preserved) and the issuer adds   W_lo * a   to the same TMEM accumulator as   W * a;
+// the activation tile gets the same treatment (a_lo, third product W * a_lo) but its product is skipped when the
+// whole tile is exactly representable (binary states always are).  W_lo * a_lo (2^-22 relative) is dropped.
 constexpr int TS_BM = 128;                 // output features per tile (MMA M)
-constexpr int TS_BK = 64;                  // reduction elements per pipeline stage
-constexpr int TS_STAGES = 4;                // maximum; fewer when the batch tile is wide (StreamArgs::stages)
-constexpr int TS_THREADS = 192;            // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
-constexpr int TS_A_BYTES = TS_BM * TS_BK * 4;
+constexpr int TS_MAX_STAGES = 8;
+constexpr int TS_NLO = 2;                  // W_lo buffers (exact mode)
+constexpr int TS_BAR_BYTES = 512;
+template <bool SPLIT> struct TsCfg {
+    static constexpr int BK = SPLIT ? 32 : 64;          // reduction elements per pipeline stage
+    static constexpr int THREADS = SPLIT ? 448 : 192;   // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue, 6-13 converters
+    static constexpr int A_BYTES = TS_BM * BK * 4;
+};
 
 struct StreamArgs {
     int M_total, K_total, B, Npad;
@@ -112,35 +123,62 @@ struct StreamArgs {
     int total_iters;
     float* part;                           // [slab][B][M_total]
     uint32_t tmem_cols;
+    int nbuf;                              // TMEM accumulator sets (2 unless the batch tile is too wide)
     int stages;
+    int blo;                               // exact mode: activation remainders are computed (0 = the caller knows them to be zero)
+    int dbg;                               // experiment switch (IMDBN_DEBUG_STREAM): 1 = converters idle, 2 = no lo products, 3 = both
+    int l2_ahead;                          // iterations whose W boxes are prefetched into L2 ahead of the ring (0 = off)
+    int w_stable;                          // W is not written by any kernel still in flight: prefetch it before the wait
     uint64_t w_policy;                     // L2 eviction priority of the W stream
     unsigned long long* trace;             // nullable (IMDBN_TS_TRACE): [cta][8] globaltimer stamps
 };
 
-__host__ __device__ inline int ts_stage_bytes(int Npad) { return TS_A_BYTES + Npad * TS_BK * 4; }
+__host__ __device__ inline int ts_bk(bool split) { return split ? 32 : 64; }
+// blo: the stage also holds the remainder tile of the activations (exact mode, activations not known to be exact)
+__host__ __device__ inline int ts_stage_bytes(int Npad, bool split, bool blo) {
+    return TS_BM * ts_bk(split) * 4 + ((split && blo) ? 2 : 1) * Npad * ts_bk(split) * 4;
+}
+__host__ __device__ inline size_t ts_smem_bytes(int Npad, int stages, bool split, bool blo) {
+    return (size_t)stages * ts_stage_bytes(Npad, split, blo) + (split ? TS_NLO * TS_BM * 32 * 4 : 0) + TS_BAR_BYTES + 1024;
+}
 
-template <bool A_MN>
-__global__ void __launch_bounds__(TS_THREADS, 1)
+// lo part of an fp32 value under tf32 truncation (exact)
+__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ float4 tf32_lo4(float4 x) {
+    return make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+}
+
+template <bool A_MN, bool SPLIT>
+__global__ void __launch_bounds__(TsCfg<SPLIT>::THREADS, 1)
 k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmB2, StreamArgs a) {
+    constexpr int TS_BK = TsCfg<SPLIT>::BK;
+    constexpr int TS_A_BYTES = TsCfg<SPLIT>::A_BYTES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int stage_bytes = ts_stage_bytes(a.Npad);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.stages * stage_bytes);
-    uint64_t* full = bars;                      // [TS_STAGES]
-    uint64_t* empty = bars + TS_STAGES;         // [TS_STAGES]
-    uint64_t* acc_full = bars + 2 * TS_STAGES;  // [2]
-    uint64_t* acc_empty = acc_full + 2;         // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    const int stage_bytes = ts_stage_bytes(a.Npad, SPLIT, a.blo != 0);
+    const int b_bytes = a.Npad * TS_BK * 4;
+    uint8_t* lo_base = smem + a.stages * stage_bytes;                 // [TS_NLO][TS_A_BYTES] (exact mode)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(lo_base + (SPLIT ? TS_NLO * TS_A_BYTES : 0));
+    uint64_t* full = bars;                      // [TS_MAX_STAGES]
+    uint64_t* empty = bars + 8;                 // [TS_MAX_STAGES]
+    uint64_t* acc_full = bars + 16;             // [2]
+    uint64_t* acc_empty = bars + 18;            // [2]
+    uint64_t* lo_full = bars + 20;              // [TS_NLO]
+    uint64_t* lo_empty = bars + 22;             // [TS_NLO]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+    volatile uint32_t* blo_flags = reinterpret_cast<volatile uint32_t*>(bars + 26);   // [TS_MAX_STAGES][4]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cta = blockIdx.x;
-    const int b0 = blockIdx.y * a.Npad;          // batches wider than 256 rows: one 256-row chunk per blockIdx.y
+    const int b0 = blockIdx.y * a.Npad;          // batches wider than Npad rows: one chunk per blockIdx.y
     const int beg = sk_beg(a.sk, cta), end = sk_beg(a.sk, cta + 1);
     const int k_iters = a.sk.k_iters;
 #define TS_MARK(i) do { if (a.trace) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.trace[(blockIdx.x + gridDim.x * blockIdx.y) * 8 + (i)] = t_; } } while (0)
 
-    pdl_trigger();
+    // A kernel that may read W before its wait must not let ITS successors run ahead of a weight update either:
+    // without w_stable the trigger follows the wait (the successor starts once everything before this kernel is done).
+    if (a.w_stable) pdl_trigger();
     if (threadIdx.x == 0) TS_MARK(0);
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -148,6 +186,7 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (a.B1) tma_prefetch_desc(&tmB2);
         for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+        for (int s = 0; s < TS_NLO; ++s) { mbar_init(&lo_full[s], 4); mbar_init(&lo_empty[s], 1); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, a.tmem_cols);
@@ -155,35 +194,68 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    pdl_wait();                 // everything above overlapped the previous kernel's tail
-    if (threadIdx.x == 0) TS_MARK(1);
+    if (!a.w_stable) { pdl_wait(); pdl_trigger(); }    // everything above overlapped the previous kernel's tail
+
+    auto load_A = [&](int it, int stage) {
+        const int tile = it / k_iters, kit = it - tile * k_iters;
+        const int m0 = tile * TS_BM, k0 = kit * TS_BK;
+        uint8_t* sA = smem + stage * stage_bytes;
+        if (A_MN) {          // W[k rows, 32 features] boxes: one per 32-feature column block
+#pragma unroll
+            for (int cb = 0; cb < TS_BM / 32; ++cb)
+                tma_load_2d_hint(sA + cb * (TS_BK * 128), &tmA, m0 + cb * 32, k0, &full[stage], a.w_policy);
+        } else {             // W[128 feature rows, 32 k] boxes: one per 32-wide k block
+#pragma unroll
+            for (int j = 0; j < TS_BK / 32; ++j)
+                tma_load_2d_hint(sA + j * (TS_BM * 128), &tmA, k0 + j * 32, m0, &full[stage], a.w_policy);
+        }
+    };
+    auto prefetch_A = [&](int it) {
+        const int tile = it / k_iters, kit = it - tile * k_iters;
+        const int m0 = tile * TS_BM, k0 = kit * TS_BK;
+        if (A_MN) {
+#pragma unroll
+            for (int cb = 0; cb < TS_BM / 32; ++cb) tma_prefetch_l2_2d(&tmA, m0 + cb * 32, k0);
+        } else {
+#pragma unroll
+            for (int j = 0; j < TS_BK / 32; ++j) tma_prefetch_l2_2d(&tmA, k0 + j * 32, m0);
+        }
+    };
+    auto load_B = [&](int it, int stage) {
+        const int tile = it / k_iters, kit = it - tile * k_iters;
+        const int k0 = kit * TS_BK;
+        uint8_t* sB = smem + stage * stage_bytes + TS_A_BYTES;
+#pragma unroll
+        for (int j = 0; j < TS_BK / 32; ++j) {
+            tma_load_2d(sB + j * (a.Npad * 128), &tmB, k0 + j * 32, b0, &full[stage]);
+            if (a.B1)      // second source matrix: its rows land behind the first one's (B1 % 8 == 0)
+                tma_load_2d(sB + j * (a.Npad * 128) + a.B1 * 128, &tmB2, k0 + j * 32, 0, &full[stage]);
+        }
+    };
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (elect_one()) {
+            const uint32_t tx = (uint32_t)(TS_A_BYTES + b_bytes);
+            int pre = 0;
+            // L2 prefetch is a hint on a coherent cache: safe even while an earlier kernel still writes W
+            const int pf0 = min(end - beg, a.stages + a.l2_ahead);
+            if (a.l2_ahead > 0) for (int i = a.w_stable ? a.stages : 0; i < pf0; ++i) prefetch_A(beg + i);
+            if (a.w_stable) {            // the weights of the first ring of stages stream in while the predecessor ends
+                pre = min(a.stages, end - beg);
+                for (int i = 0; i < pre; ++i) { mbar_expect_tx(&full[i], tx); load_A(beg + i, i); }
+                pdl_wait();
+            }
+            TS_MARK(1);
             int stage = 0; uint32_t phase = 0;
             for (int it = beg; it < end; ++it) {
-                const int tile = it / k_iters, kit = it - tile * k_iters;
-                const int m0 = tile * TS_BM, k0 = kit * TS_BK;
-                uint8_t* sA = smem + stage * stage_bytes;
-                uint8_t* sB = sA + TS_A_BYTES;
-                mbar_wait(&empty[stage], phase ^ 1);
-                mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
-                if (A_MN) {          // W[k rows, 32 features] boxes: one per 32-feature column block
-#pragma unroll
-                    for (int cb = 0; cb < TS_BM / 32; ++cb)
-                        tma_load_2d_hint(sA + cb * (TS_BK * 128), &tmA, m0 + cb * 32, k0, &full[stage], a.w_policy);
-                } else {             // W[128 feature rows, 32 k] boxes: one per 32-wide k block
-#pragma unroll
-                    for (int j = 0; j < TS_BK / 32; ++j)
-                        tma_load_2d_hint(sA + j * (TS_BM * 128), &tmA, k0 + j * 32, m0, &full[stage], a.w_policy);
+                if (a.l2_ahead > 0 && it + a.stages + a.l2_ahead < end) prefetch_A(it + a.stages + a.l2_ahead);
+                if (it - beg >= pre) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full[stage], tx);
+                    load_A(it, stage);
                 }
-#pragma unroll
-                for (int j = 0; j < TS_BK / 32; ++j) {
-                    tma_load_2d(sB + j * (a.Npad * 128), &tmB, k0 + j * 32, b0, &full[stage]);
-                    if (a.B1)      // second source matrix: its rows land behind the first one's (B1 % 8 == 0)
-                        tma_load_2d(sB + j * (a.Npad * 128) + a.B1 * 128, &tmB2, k0 + j * 32, 0, &full[stage]);
-                }
+                load_B(it, stage);
                 if (++stage == a.stages) { stage = 0; phase ^= 1; }
             }
         }
@@ -191,56 +263,100 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // ===================== MMA issuer (one thread) =====================
         if (elect_one()) {
             const uint32_t idesc = idesc_tf32(TS_BM, a.Npad, A_MN, false, false);
+            auto a_desc = [&](uint32_t sA, int g) -> uint64_t {
+                if (A_MN)   // k-group g = rows 8g..8g+7 (two 4-row swizzle atoms) of every column-block box
+                    return smem_desc(sA + g * 1024, TS_BK * 128, 512, LAYOUT_SW128_BASE32B);
+                // K-major: 32-wide k block g/4, 32-byte step inside the swizzle row
+                return smem_desc(sA + (g / 4) * (TS_BM * 128) + (g % 4) * 32, 16, 1024, LAYOUT_SW128);
+            };
+            auto b_desc = [&](uint32_t sB, int g) -> uint64_t {
+                return smem_desc(sB + (g / 4) * (a.Npad * 128) + (g % 4) * 32, 16, 1024, LAYOUT_SW128);
+            };
             int stage = 0; uint32_t phase = 0;
-            int seg = 0;
+            // exact mode: the lo products of iteration n are issued after the hi products of iteration n+1, so the
+            // converters work on a tile while the tensor pipe is busy with its neighbours
+            int p_stage = -1, p_n = 0, p_buf = 0; bool p_last = false, p_first = false; uint32_t p_tmem = 0;
+            auto issue_lo = [&]() {
+                const int l = p_n & (TS_NLO - 1);
+                mbar_wait(&lo_full[l], (p_n / TS_NLO) & 1);
+                tc_fence_after();
+                const uint32_t sA = smem_u32(smem + p_stage * stage_bytes);
+                const uint32_t sB = sA + TS_A_BYTES, sBlo = sB + (uint32_t)b_bytes;
+                const uint32_t sAlo = smem_u32(lo_base + l * TS_A_BYTES);
+                const uint32_t blo = a.blo ? (blo_flags[p_stage * 4] | blo_flags[p_stage * 4 + 1] | blo_flags[p_stage * 4 + 2] |
+                                              blo_flags[p_stage * 4 + 3]) : 0u;
+                // the remainder products (2^-11 of the main ones) have their own accumulator: added to the large
+                // running sum one by one they would each cost it a truncation
+                const uint32_t d_lo = p_tmem + (uint32_t)a.Npad;
+                if (!(a.dbg & 2) || p_first)
+#pragma unroll
+                for (int g = 0; g < TS_BK / 8; ++g)
+                    mma_tf32(d_lo, a_desc(sAlo, g), b_desc(sB, g), idesc, (p_first && g == 0) ? 0u : 1u);
+                if (blo && !(a.dbg & 2)) {
+#pragma unroll
+                    for (int g = 0; g < TS_BK / 8; ++g) mma_tf32(d_lo, a_desc(sA, g), b_desc(sBlo, g), idesc, 1u);
+                }
+                mma_commit(&empty[p_stage]);
+                mma_commit(&lo_empty[l]);
+                if (p_last) mma_commit(&acc_full[p_buf]);
+            };
+            int seg = 0, n = 0;
             for (int cur = beg; cur < end; ++seg) {
                 const int tile = cur / k_iters, kit0 = cur - tile * k_iters;
                 const int n_it = min(end - cur, k_iters - kit0);
-                const int buf = seg & 1;
-                mbar_wait(&acc_empty[buf], ((seg >> 1) & 1) ^ 1);
+                const int buf = seg % a.nbuf;
+                // one accumulator set: the previous segment's deferred products must be issued (and its accumulator
+                // handed to the epilogue) before this segment can wait for the set to be drained
+                if (SPLIT && a.nbuf == 1 && p_stage >= 0) { issue_lo(); p_stage = -1; }
+                mbar_wait(&acc_empty[buf], ((seg / a.nbuf) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * a.Npad);
-                for (int i = 0; i < n_it; ++i) {
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * (SPLIT ? 2 : 1) * a.Npad);
+                for (int i = 0; i < n_it; ++i, ++n) {
                     mbar_wait(&full[stage], phase);
                     if (cur == beg && i == 0) TS_MARK(2);
                     tc_fence_after();
                     const uint32_t sA = smem_u32(smem + stage * stage_bytes);
                     const uint32_t sB = sA + TS_A_BYTES;
 #pragma unroll
-                    for (int g = 0; g < TS_BK / 8; ++g) {       // one MMA per 8 k (tf32 UMMA_K)
-                        uint64_t ad, bd;
-                        if (A_MN)   // k-group g = rows 8g..8g+7 (two 4-row swizzle atoms) of every column-block box
-                            ad = smem_desc(sA + g * 1024, TS_BK * 128, 512, LAYOUT_SW128_BASE32B);
-                        else        // K-major: 32-wide k block g/4, 32-byte step inside the swizzle row
-                            ad = smem_desc(sA + (g / 4) * (TS_BM * 128) + (g % 4) * 32, 16, 1024, LAYOUT_SW128);
-                        bd = smem_desc(sB + (g / 4) * (a.Npad * 128) + (g % 4) * 32, 16, 1024, LAYOUT_SW128);
-                        mma_tf32(d_tmem, ad, bd, idesc, (i | g) != 0);
+                    for (int g = 0; g < TS_BK / 8; ++g)         // one MMA per 8 k (tf32 UMMA_K)
+                        mma_tf32(d_tmem, a_desc(sA, g), b_desc(sB, g), idesc, (i | g) != 0);
+                    if (SPLIT) {
+                        if (p_stage >= 0) issue_lo();
+                        p_stage = stage; p_n = n; p_buf = buf; p_last = (i == n_it - 1); p_first = (i == 0); p_tmem = d_tmem;
+                    } else {
+                        mma_commit(&empty[stage]);                  // smem slot free when these MMAs retire
                     }
-                    mma_commit(&empty[stage]);                  // smem slot free when these MMAs retire
                     if (++stage == a.stages) { stage = 0; phase ^= 1; }
                 }
-                mma_commit(&acc_full[buf]);
+                if (!SPLIT) mma_commit(&acc_full[buf]);
                 cur += n_it;
             }
+            if (SPLIT && p_stage >= 0) issue_lo();
             TS_MARK(3);
         }
-    } else {
+    } else if (warp < 6) {
         // ===================== epilogue: TMEM -> partial slab =====================
         const int quad = warp & 3;                               // TMEM lane quadrant this warp may read
         int seg = 0;
         for (int cur = beg; cur < end; ++seg) {
             const int tile = cur / k_iters, kit0 = cur - tile * k_iters;
             const int n_it = min(end - cur, k_iters - kit0);
-            const int buf = seg & 1;
+            const int buf = seg % a.nbuf;
             const int slab = cta - sk_cta_of(a.sk, tile * k_iters);
-            mbar_wait(&acc_full[buf], (seg >> 1) & 1);
+            mbar_wait(&acc_full[buf], (seg / a.nbuf) & 1);
             tc_fence_after();
             const int m = tile * TS_BM + quad * 32 + lane;
             float* dst = a.part + ((size_t)slab * a.B + b0) * a.M_total + m;
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * a.Npad);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * (SPLIT ? 2 : 1) * a.Npad);
             for (int c0 = 0; c0 < a.Npad; c0 += 16) {
                 float v[16];
                 tmem_ld16(taddr + c0, v);
+                if (SPLIT) {
+                    float w[16];
+                    tmem_ld16(taddr + a.Npad + c0, w);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] += w[i];
+                }
                 if (m < a.M_total) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
@@ -252,6 +368,39 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
             cur += n_it;
             if (warp == 2 && lane == 0) TS_MARK(4 + min(seg, 1));
+        }
+    } else if (SPLIT) {
+        // ===================== converters (exact mode): lo tiles of W and of the activations =====================
+        // Two groups of four warps; group g converts the iterations n with n % 2 == g into W_lo buffer g, so two
+        // tiles are in conversion at any time (the per-tile latency -- shared-memory round trip, proxy fence,
+        // barrier hand-over -- is several times the issue time).
+        const int ct = (threadIdx.x - 192) & 127, cw = ct >> 5, grp = (threadIdx.x - 192) >> 7;
+        const int nB4 = b_bytes / 16;
+        for (int it = beg + grp, n = grp; it < end; it += TS_NLO, n += TS_NLO) {
+            const int stage = n % a.stages;
+            const uint32_t phase = (uint32_t)(n / a.stages) & 1u;
+            const float4* sA = reinterpret_cast<const float4*>(smem + stage * stage_bytes);
+            const float4* sB = reinterpret_cast<const float4*>(smem + stage * stage_bytes + TS_A_BYTES);
+            float4* sBlo = reinterpret_cast<float4*>(smem + stage * stage_bytes + TS_A_BYTES + b_bytes);
+            float4* sAlo = reinterpret_cast<float4*>(lo_base + grp * TS_A_BYTES);
+            mbar_wait(&full[stage], phase);
+            mbar_wait(&lo_empty[grp], ((n / TS_NLO) & 1) ^ 1);
+            bool nz = false;
+            if (!(a.dbg & 1)) {
+#pragma unroll
+                for (int i = 0; i < TS_A_BYTES / 16 / 128; ++i) sAlo[ct + i * 128] = tf32_lo4(sA[ct + i * 128]);
+                if (a.blo)
+                for (int i = ct; i < nB4; i += 128) {
+                    const float4 lo = tf32_lo4(sB[i]);
+                    nz |= (lo.x != 0.0f) | (lo.y != 0.0f) | (lo.z != 0.0f) | (lo.w != 0.0f);
+                    sBlo[i] = lo;
+                }
+            }
+            nz = __any_sync(0xffffffffu, nz);
+            if (lane == 0) blo_flags[stage * 4 + cw] = nz ? 1u : 0u;
+            if (!(a.dbg & 4)) fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's smem reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&lo_full[grp]);
         }
     }
 
@@ -288,6 +437,7 @@ static inline uint64_t l2_policy_for(const imdbn_rbm* r) {
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static inline int npad_of(int B) { return std::max(16, (B + 15) / 16 * 16); }
 static inline uint32_t pow2_cols(int n) { uint32_t c = 32; while ((int)c < n) c <<= 1; return c; }
+static inline bool tc_split(const imdbn_ctx* ctx) { return ctx->precision == IMDBN_PREC_TF32X2; }
 
 bool tc_shape_ok(const imdbn_rbm* r, int B) {
     return r->V % 4 == 0 && r->H % 4 == 0 && aligned16(r->W) && B >= 1;
@@ -300,15 +450,15 @@ bool tc_down_supported(const imdbn_ctx* ctx, const imdbn_rbm* r, int B) { return
 bool tc_stats_supported(const imdbn_ctx* ctx, const imdbn_rbm* r, int B) {
     return tc_shape_ok(r, B) && tc_state(const_cast<imdbn_ctx*>(ctx))->encode != nullptr;
 }
-size_t tc_ws_bytes(const imdbn_ctx*, const imdbn_rbm*, int) { return 0; }
 
 SKPlan tc_plan(const imdbn_ctx* ctx, int M_total, int K_total) {
     SKPlan p;
+    const int bk = ts_bk(tc_split(ctx));
     const int m_tiles = (M_total + TS_BM - 1) / TS_BM;
-    p.k_iters = (K_total + TS_BK - 1) / TS_BK;
+    p.k_iters = (K_total + bk - 1) / bk;
     const int total = m_tiles * p.k_iters;
-    // at least 4 k-iterations per CTA: fewer, longer ranges for small layers (fewer slabs to add)
-    const int G = std::max(1, std::min(tc_sms(ctx), total / 4));
+    // at least 256 reduction elements per CTA: fewer, longer ranges for small layers (fewer slabs to add)
+    const int G = std::max(1, std::min(tc_sms(ctx), total / (256 / bk)));
     p.q = total / G;
     p.r = total % G;
     p.tile_w = TS_BM;
@@ -327,16 +477,17 @@ int tc_plan_max_slabs(const SKPlan& p, int M_total) {
     return mx;
 }
 
-template <bool A_MN>
+template <bool A_MN, bool SPLIT>
 static int launch_stream(imdbn_ctx* ctx, const CUtensorMap* tmA, const CUtensorMap* tmB, const CUtensorMap* tmB2,
                          StreamArgs& a, int G, int chunks, cudaStream_t st) {
-    const size_t smem = (size_t)a.stages * ts_stage_bytes(a.Npad) + 1024 + 256;
+    const size_t smem = ts_smem_bytes(a.Npad, a.stages, SPLIT, a.blo != 0);
     static size_t smem_set = 0;          // the attribute is sticky: raise it only when a larger size is needed
     if (smem > smem_set) {
-        IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_tc_stream<A_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_tc_stream<A_MN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
-    IMDBN_CUDA(ctx, launch_pdl(k_tc_stream<A_MN>, dim3(G, chunks), dim3(TS_THREADS), smem, st, *tmA, *tmB, *tmB2, a));
+    IMDBN_CUDA(ctx, launch_pdl(k_tc_stream<A_MN, SPLIT>, dim3(G, chunks), dim3(TsCfg<SPLIT>::THREADS), smem, st, *tmA, *tmB,
+                               *tmB2, a));
     IMDBN_CHECK_LAUNCH(ctx, "k_tc_stream");
     return 0;
 }
@@ -346,18 +497,26 @@ static int stream_pass(imdbn_ctx* ctx, const imdbn_rbm* r, const float* act, int
                        cudaStream_t st, const float* act2 = nullptr, int B1 = 0) {
     const int M_total = up ? r->H : r->V, K_total = up ? r->V : r->H;
     if (!aligned16(act)) return fail(ctx, -1, "tc pass: activation pointer must be 16-byte aligned");
+    const bool split = tc_split(ctx);
+    const int bk = ts_bk(split);
     StreamArgs a{};
     a.M_total = M_total; a.K_total = K_total; a.B = B; a.Npad = B > 256 ? 256 : npad_of(B);
     const int chunks = (B + a.Npad - 1) / a.Npad;
     a.sk = tc_plan(ctx, M_total, K_total);
     a.total_iters = ((M_total + TS_BM - 1) / TS_BM) * a.sk.k_iters;
     a.part = part;
-    a.tmem_cols = pow2_cols(2 * a.Npad);
+    a.nbuf = (split ? 4 : 2) * a.Npad <= 512 ? 2 : 1;
+    a.tmem_cols = pow2_cols(a.nbuf * (split ? 2 : 1) * a.Npad);
     a.w_policy = l2_policy_for(r);
-    a.stages = std::max(2, std::min(TS_STAGES, (200 * 1024) / ts_stage_bytes(a.Npad)));
+    a.w_stable = ctx->w_stable ? 1 : 0;
+    a.blo = (split && !ctx->act_exact) ? 1 : 0;
+    { static const int dbg_env = getenv("IMDBN_DEBUG_STREAM") ? atoi(getenv("IMDBN_DEBUG_STREAM")) : 0; a.dbg = dbg_env; }
+    { static const int pf_env = getenv("IMDBN_L2_AHEAD") ? atoi(getenv("IMDBN_L2_AHEAD")) : 0; a.l2_ahead = pf_env * (64 / bk); }
+    const int budget = 226 * 1024 - TS_BAR_BYTES - (split ? TS_NLO * TS_BM * 32 * 4 : 0);
+    a.stages = std::max(2, std::min(split ? TS_MAX_STAGES : 4, budget / ts_stage_bytes(a.Npad, split, a.blo != 0)));
     const int G = tc_plan_ctas(a.sk, M_total);
-    // W is [V, H] row-major: inner = H.  up: boxes [64 k-rows x 32 h]; down: boxes [128 v-rows x 32 h]
-    const CUtensorMap* tmA = get_map(ctx, r->W, r->H, r->V, up ? TS_BK : TS_BM, up);
+    // W is [V, H] row-major: inner = H.  up: boxes [bk k-rows x 32 h]; down: boxes [128 v-rows x 32 h]
+    const CUtensorMap* tmA = get_map(ctx, r->W, r->H, r->V, up ? bk : TS_BM, up);
     const CUtensorMap* tmB = nullptr;
     const CUtensorMap* tmB2 = nullptr;
     if (act2) {
@@ -381,8 +540,11 @@ static int stream_pass(imdbn_ctx* ctx, const imdbn_rbm* r, const float* act, int
         cudaMemsetAsync(trace_buf, 0, 148 * 8 * 8, st);
         a.trace = trace_buf;
     }
-    int rc = up ? launch_stream<true>(ctx, tmA, tmB, tmB2, a, G, chunks, st)
-                : launch_stream<false>(ctx, tmA, tmB, tmB2, a, G, chunks, st);
+    int rc;
+    if (split) rc = up ? launch_stream<true, true>(ctx, tmA, tmB, tmB2, a, G, chunks, st)
+                       : launch_stream<false, true>(ctx, tmA, tmB, tmB2, a, G, chunks, st);
+    else       rc = up ? launch_stream<true, false>(ctx, tmA, tmB, tmB2, a, G, chunks, st)
+                       : launch_stream<false, false>(ctx, tmA, tmB, tmB2, a, G, chunks, st);
     if (traced && rc == 0) {
         static unsigned long long h[148 * 8];
         cudaStreamSynchronize(st);
@@ -408,6 +570,27 @@ int tc_gemm_down(imdbn_ctx* ctx, const imdbn_rbm* r, const float* h, int B, floa
     return stream_pass(ctx, r, h, B, part, false, st);
 }
 
+// tile shape: HBM-bound small batches stream W / W_m through 128 x 128 tiles with packed operands; from 512 rows the
+// kernel is tensor-bound and uses 128 x 256 tiles fed by TMA (the exact mode always takes the narrow shape)
+static bool stats_wide(const imdbn_ctx* ctx, const imdbn_rbm* r, int B) {
+    static const bool narrow_env = getenv("IMDBN_STATS_NARROW") != nullptr;
+    return !tc_split(ctx) && B >= 512 && r->H >= 256 && !narrow_env;
+}
+struct PackSizes { size_t pa, pa_lo, pb, total; };
+static PackSizes pack_sizes(const imdbn_rbm* r, int B, bool split) {
+    const size_t mt = (r->V + ST_BM - 1) / ST_BM, nt = (r->H + 127) / 128, kc = (B + ST_KC - 1) / ST_KC;
+    PackSizes p;
+    p.pa = mt * kc * 2 * ST_SEG_A;
+    p.pa_lo = split ? p.pa : 0;
+    p.pb = nt * kc * (split ? 4 : 2) * st_seg_b<128>();
+    p.total = p.pa + p.pa_lo + p.pb;
+    return p;
+}
+size_t tc_ws_bytes(const imdbn_ctx* ctx, const imdbn_rbm* r, int B) {
+    if (!uses_tc(ctx) || !tc_shape_ok(r, B) || stats_wide(ctx, r, B)) return 0;
+    return pack_sizes(r, B, tc_split(ctx)).total + 512;
+}
+
 int tc_gemm_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* vp, const float* hp, const float* vn,
                   const float* hn, int B, float* dS_out, const imdbn_update* upd, cudaStream_t st) {
     if (!aligned16(vp) || !aligned16(hp) || !aligned16(vn) || !aligned16(hn) || (dS_out && !aligned16(dS_out)) ||
@@ -415,7 +598,8 @@ int tc_gemm_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* vp, const flo
         return fail(ctx, -1, "tc stats: pointers must be 16-byte aligned");
     // tile shape: HBM-bound small batches stream W / W_m through 128 x 128 tiles and four IO slots; from 512 rows
     // the kernel is tensor-bound and uses 128 x 256 tiles (more MACs per operand byte), three operand stages
-    const bool wide = B >= 512 && r->H >= 256 && getenv("IMDBN_STATS_NARROW") == nullptr;
+    const bool split = tc_split(ctx);
+    const bool wide = stats_wide(ctx, r, B);
     const int BN = wide ? 256 : 128;
     StatsArgs a{};
     a.V = r->V; a.H = r->H; a.B = B;
@@ -424,17 +608,41 @@ int tc_gemm_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* vp, const flo
     a.k_chunks = (B + ST_KC - 1) / ST_KC;
     if (upd) { a.lr = upd->lr; a.mom = upd->momentum; a.wd = upd->weight_decay; a.bsz = (float)upd->batch_global; }
     { static const int dbg_env = getenv("IMDBN_DEBUG_STATS") ? atoi(getenv("IMDBN_DEBUG_STATS")) : 0; a.dbg = dbg_env; }
-    a.late_wait = ctx->stats_after_colstats ? 1 : 0;
+    const bool after_colstats = ctx->stats_after_colstats;
+    a.late_wait = after_colstats ? 1 : 0;
     ctx->stats_after_colstats = false;
     a.w_policy = l2_policy_for(r);
     a.wm_policy = l2_policy_for(r);
-    const CUtensorMap* tVP = get_map(ctx, vp, r->V, B, ST_KC, true);
-    const CUtensorMap* tVN = get_map(ctx, vn, r->V, B, ST_KC, true);
-    const CUtensorMap* tHP = get_map(ctx, hp, r->H, B, ST_KC, true);
-    const CUtensorMap* tHN = get_map(ctx, hn, r->H, B, ST_KC, true);
     const CUtensorMap* tW = get_map(ctx, dS_out ? dS_out : r->W, r->H, r->V, ST_BM, false);
     const CUtensorMap* tWm = dS_out ? tW : get_map(ctx, r->Wm, r->H, r->V, ST_BM, false);
+    // operand maps: only the wide (TMA-fed) variant reads them
+    const CUtensorMap* tVP = wide ? get_map(ctx, vp, r->V, B, ST_KC, true) : tW;
+    const CUtensorMap* tVN = wide ? get_map(ctx, vn, r->V, B, ST_KC, true) : tW;
+    const CUtensorMap* tHP = wide ? get_map(ctx, hp, r->H, B, ST_KC, true) : tW;
+    const CUtensorMap* tHN = wide ? get_map(ctx, hn, r->H, B, ST_KC, true) : tW;
     if (!tVP || !tVN || !tHP || !tHN || !tW || !tWm) return fail(ctx, -5, "cuTensorMapEncodeTiled failed");
+    if (!wide) {
+        // pack the operands into tile-ready images (workspace from the arena of the current API call)
+        const PackSizes ps = pack_sizes(r, B, split);
+        uint8_t* ws = arena_take<uint8_t>(ctx, ps.total);
+        if (ctx->arena.off > ctx->arena.cap) return fail(ctx, -2, "tc stats: workspace not reserved (tc_ws_bytes)");
+        if (!ctx->pack_flags) {
+            IMDBN_CUDA(ctx, cudaMalloc((void**)&ctx->pack_flags, 256));
+            IMDBN_CUDA(ctx, cudaMemsetAsync(ctx->pack_flags, 0, 256, st));
+        }
+        PackArgs pk{};
+        pk.vp = vp; pk.vn = vn; pk.hp = hp; pk.hn = hn;
+        pk.B = B; pk.V = r->V; pk.H = r->H; pk.m_tiles = a.m_tiles; pk.n_tiles = a.n_tiles; pk.k_chunks = a.k_chunks;
+        pk.split = split ? 1 : 0;
+        pk.pa = ws; pk.pa_lo = ws + ps.pa; pk.pb = ws + ps.pa + ps.pa_lo;
+        pk.flags = ctx->pack_flags; pk.gen = ++ctx->pack_gen;
+        if (pk.gen == 0) pk.gen = ++ctx->pack_gen;                 // 0 = the memset value, never a valid generation
+        pk.after_colstats = after_colstats ? 1 : 0;
+        const int n4 = (a.m_tiles + a.n_tiles) * 32;
+        IMDBN_CUDA(ctx, launch_pdl(k_pack_ops, dim3((n4 + 255) / 256, a.k_chunks * ST_KC), dim3(256), 0, st, pk));
+        IMDBN_CHECK_LAUNCH(ctx, "k_pack_ops");
+        a.pa = pk.pa; a.pa_lo = pk.pa_lo; a.pb = pk.pb; a.flags = pk.flags; a.gen = pk.gen;
+    }
     const int G = std::min(tc_sms(ctx), a.m_tiles * a.n_tiles);
     auto launch = [&](auto kernel, int smem, bool& attr_set) -> cudaError_t {
         if (!attr_set) {
@@ -444,14 +652,17 @@ int tc_gemm_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* vp, const flo
         }
         return launch_pdl(kernel, dim3(G), dim3(ST_THREADS), (size_t)smem, st, *tVP, *tVN, *tHP, *tHN, *tW, *tWm, a);
     };
-    static bool set[4] = {false, false, false, false};
+    static bool set[6] = {false, false, false, false, false, false};
     cudaError_t e;
-    if (wide)
-        e = dS_out ? launch(k_tc_stats<false, 256, 3, 2>, st_smem<256, 3, 2>(), set[0])
-                   : launch(k_tc_stats<true, 256, 3, 2>, st_smem<256, 3, 2>(), set[1]);
+    if (split)
+        e = dS_out ? launch(k_tc_stats<false, 128, 2, 4, true, true>, st_smem<128, 2, 4, true>(), set[4])
+                   : launch(k_tc_stats<true, 128, 2, 4, true, true>, st_smem<128, 2, 4, true>(), set[5]);
+    else if (wide)
+        e = dS_out ? launch(k_tc_stats<false, 256, 3, 2, false, false>, st_smem<256, 3, 2, false>(), set[0])
+                   : launch(k_tc_stats<true, 256, 3, 2, false, false>, st_smem<256, 3, 2, false>(), set[1]);
     else
-        e = dS_out ? launch(k_tc_stats<false, 128, 2, 4>, st_smem<128, 2, 4>(), set[2])
-                   : launch(k_tc_stats<true, 128, 2, 4>, st_smem<128, 2, 4>(), set[3]);
+        e = dS_out ? launch(k_tc_stats<false, 128, 3, 4, true, false>, st_smem<128, 3, 4, false>(), set[2])
+                   : launch(k_tc_stats<true, 128, 3, 4, true, false>, st_smem<128, 3, 4, false>(), set[3]);
     IMDBN_CUDA(ctx, e);
     IMDBN_CHECK_LAUNCH(ctx, "k_tc_stats");
     return 0;

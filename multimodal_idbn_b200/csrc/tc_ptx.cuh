@@ -78,6 +78,18 @@ __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const void* tma
           "l"(policy)
         : "memory");
 }
+// 1-D bulk copy global -> shared (size % 16 == 0, both addresses 16-byte aligned), completion on an mbarrier
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// L2 prefetch of one box (no shared memory, no completion): raises the bytes in flight from HBM beyond what the
+// shared-memory ring can hold, so the ring's loads find their data in L2
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
+                 ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_store_2d_hint(const void* tmap, int c0, int c1, const void* smem_src,
                                                   uint64_t policy) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"

@@ -4,13 +4,20 @@
 //   W_m <- mom W_m + lr (dS/bsz - wd W) ;  W <- W + W_m                   (rbm.py:212-213)
 //
 // Output-streaming and HBM-bound at small batch: per 128 x 128 tile the kernel reads and writes
-// 2 x 64 KB of W / W_m and needs only 16 tf32 MMAs.  Every byte therefore moves through TMA:
-//   * operand producer (warp 0): [16 batch rows x 32] boxes of vp, vn, hp, hn (MN-major, 32-byte-atom
-//     swizzle) into a 2-stage ring;
-//   * MMA issuer (warp 1): 128x128x8 tcgen05.mma kind::tf32 into one of two TMEM accumulators; the
-//     negative phase is subtracted with the a_negate bit;
-//   * IO producer (warp 2): the W and W_m half-tiles (128 rows x 64 columns each) into one of two 64 KB
-//     slots -- up to 128 KB of weight traffic in flight per SM, independent of the math warps;
+// 2 x 64 KB of W / W_m and needs only a handful of tf32 MMAs.  Roles:
+//   * operand producer (warp 0).  Both operands are MN-major (feature index contiguous in memory, batch index = K),
+//     16 batch rows per stage.
+//       - narrow variants (PACK; 128 x 128 tiles, batch < 512): the operands were packed by k_pack_ops (below) into
+//         tile-ready images, a stage is two bulk copies;
+//       - wide variant (128 x 256 tiles, tensor-bound large batches): TMA boxes of [16 batch rows x 32 floats]
+//         straight from the activation matrices, 3-stage ring.
+//     Exact mode (SPLIT): the stage also carries the tf32 remainders h_lo of the hidden operands and the issuer adds
+//     v * h_lo; when some v is not exactly representable (never for binary states) every tile gets a second round
+//     of chunks  v_lo * h  (see k_tc_stream for the arithmetic).
+//   * MMA issuer (warp 1): tcgen05.mma kind::tf32 into one of two TMEM accumulators; the negative phase is
+//     subtracted with the a_negate bit;
+//   * IO producer (warp 2): the W and W_m slices (128 rows x 32 columns each) into one of the 32 KB slots -- up to
+//     128 KB of weight traffic in flight per SM, independent of the math warps;
 //   * epilogue (warps 4-11): thread = tile row; accumulator from TMEM, W / W_m from the swizzled slot
 //     (bank-conflict-free with one row per lane), update written back in place;
 //   * store issuer (warp 3): TMA-stores the slot back to W / W_m (edges are clipped by the tensor map)
@@ -18,41 +25,110 @@
 #pragma once
 
 constexpr int ST_BM = 128;                 // visible units per tile (MMA M)
-constexpr int ST_KC = 16;                  // batch rows per operand stage
 constexpr int ST_THREADS = 384;            // 12 warps, roles above
 constexpr int ST_EPI_WARPS = 8;
+constexpr int ST_KC = 16;                  // batch rows per operand stage
 constexpr int ST_OP_BOX = ST_KC * 128;                 // one [16 x 32 floats] box = 2 KB
 constexpr int ST_SEG_A = (ST_BM / 32) * ST_OP_BOX;     // 8 KB
 constexpr int ST_IO_BOX = ST_BM * 128;                 // [128 rows x 32 floats] = 16 KB
 constexpr int ST_SLOT_BYTES = 2 * ST_IO_BOX;           // W + W_m column slice [128 x 32] each: 32 KB
-// Two shapes of the same kernel:
-//   small batch (HBM-bound, the update streams W / W_m): 128 x 128 tiles, 2 operand stages, 4 IO slots;
-//   large batch (tensor-bound, B >= 512): 128 x 256 tiles (21 MACs per operand byte instead of 16), 3 operand
-//   stages, 2 IO slots -- the weight traffic is negligible there.
 template <int BN> __host__ __device__ constexpr int st_seg_b() { return (BN / 32) * ST_OP_BOX; }
-template <int BN> __host__ __device__ constexpr int st_stage_bytes() { return 2 * (ST_SEG_A + st_seg_b<BN>()); }   // positive + negative phase
-template <int BN, int STAGES, int NSLOT> __host__ __device__ constexpr int st_smem() {
-    return STAGES * st_stage_bytes<BN>() + NSLOT * ST_SLOT_BYTES + 1024 /*barriers*/ + 1024 /*align*/;
+// stage = [vp | vn | hp | hn] and, in the exact mode, [| hp_lo | hn_lo]
+template <int BN, bool SPLIT> __host__ __device__ constexpr int st_stage_bytes() {
+    return 2 * ST_SEG_A + (SPLIT ? 4 : 2) * st_seg_b<BN>();
+}
+template <int BN, int STAGES, int NSLOT, bool SPLIT> __host__ __device__ constexpr int st_smem() {
+    return STAGES * st_stage_bytes<BN, SPLIT>() + NSLOT * ST_SLOT_BYTES + 1024 /*barriers*/ + 1024 /*align*/;
 }
 
 struct StatsArgs {
     int V, H, B;
     int m_tiles, n_tiles, k_chunks;
     float lr, mom, wd, bsz;
+    // PACK variants: operand images written by k_pack_ops (one contiguous piece per (tile row / column, chunk))
+    const uint8_t* pa; const uint8_t* pa_lo; const uint8_t* pb;
+    const uint32_t* flags; uint32_t gen;          // flags[0] == gen: some v value is not exactly representable in tf32
     uint64_t w_policy, wm_policy;   // L2 eviction priorities of the W and W_m streams
     int late_wait;
     int dbg;    // experiment switch (IMDBN_DEBUG_STATS): 1 = no operands/MMA, 2 = no W/W_m traffic
 };
 
-template <bool UPDATE, int ST_BN, int ST_STAGES, int ST_NSLOT>
+// ---- operand packing ------------------------------------------------------------------------------------------
+// The statistics operands are MN-major for the tensor core (feature index contiguous, batch index = K): with TMA that
+// means boxes of only [rows x 32 floats] -- ~100 two-kilobyte boxes per 128 x 128 tile, whose issue cost rivals the
+// 16 big weight boxes of the tile on the SM's one TMA unit.  At small batch (the HBM-bound regime) the activations are
+// tiny, so one pass over them writes, per (128-column block, 16-row chunk), the exact shared-memory image the MMA
+// wants (32-byte-atom swizzle, Swizzle<2,5,2> on byte offsets: element (k, c) of a [16 x 32] box at
+// k * 128 + (((c / 8) ^ (k & 3)) * 32) + (c % 8) * 4), zero-padded at the edges; the statistics kernel then fetches a
+// whole stage with two bulk copies.  In the exact mode the same pass writes the tf32 remainders x - trunc19(x): of h
+// into the same piece (always multiplied), of v into a twin image that is only multiplied when some remainder is
+// non-zero (flags[0] = gen) -- binary states never are.
+struct PackArgs {
+    const float* vp; const float* vn; const float* hp; const float* hn;
+    int B, V, H, m_tiles, n_tiles, k_chunks, split;
+    uint8_t* pa; uint8_t* pa_lo; uint8_t* pb;
+    uint32_t* flags; uint32_t gen;
+    int after_colstats;      // the predecessor triggered only after its own wait: dependents may be released at once
+};
+
+__global__ void __launch_bounds__(256) k_pack_ops(PackArgs a) {
+    if (a.after_colstats) pdl_trigger();
+    pdl_wait();
+    if (!a.after_colstats) pdl_trigger();
+    const int r = blockIdx.y;                                      // batch row (padded to k_chunks * 16)
+    const int c4 = blockIdx.x * blockDim.x + threadIdx.x;          // float4 column over [A side | B side]
+    const int na4 = a.m_tiles * 32, nb4 = a.n_tiles * 32;
+    if (c4 >= na4 + nb4) return;
+    const int kc = r / ST_KC, k = r % ST_KC;
+    const bool is_a = c4 < na4;
+    const int q = is_a ? c4 : c4 - na4;                            // float4 column inside its side
+    const int tile = q >> 5, cb = (q >> 3) & 3, j = q & 7;
+    const uint32_t box_off = (uint32_t)cb * ST_OP_BOX + (uint32_t)k * 128u +
+                             ((((uint32_t)j >> 1) ^ (uint32_t)(k & 3)) << 5) + (((uint32_t)j & 1u) << 4);
+    const int col = 4 * q, W = is_a ? a.V : a.H;
+    const bool valid = r < a.B && col < W;
+    const float* s0 = is_a ? a.vp : a.hp;
+    const float* s1 = is_a ? a.vn : a.hn;
+    float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+    if (valid) {
+        x0 = *reinterpret_cast<const float4*>(s0 + (size_t)r * W + col);
+        x1 = *reinterpret_cast<const float4*>(s1 + (size_t)r * W + col);
+    }
+    if (is_a) {
+        const size_t piece = ((size_t)tile * a.k_chunks + kc) * (2 * ST_SEG_A);
+        *reinterpret_cast<float4*>(a.pa + piece + box_off) = x0;
+        *reinterpret_cast<float4*>(a.pa + piece + ST_SEG_A + box_off) = x1;
+        if (a.split) {
+            const float4 l0 = tf32_lo4(x0), l1 = tf32_lo4(x1);
+            *reinterpret_cast<float4*>(a.pa_lo + piece + box_off) = l0;
+            *reinterpret_cast<float4*>(a.pa_lo + piece + ST_SEG_A + box_off) = l1;
+            const bool nz = (l0.x != 0.f) | (l0.y != 0.f) | (l0.z != 0.f) | (l0.w != 0.f) |
+                            (l1.x != 0.f) | (l1.y != 0.f) | (l1.z != 0.f) | (l1.w != 0.f);
+            if (nz) a.flags[0] = a.gen;                            // (every writer stores the same value)
+        }
+    } else {
+        constexpr int SEG_B = st_seg_b<128>();
+        const size_t piece = ((size_t)tile * a.k_chunks + kc) * ((a.split ? 4 : 2) * SEG_B);
+        *reinterpret_cast<float4*>(a.pb + piece + box_off) = x0;
+        *reinterpret_cast<float4*>(a.pb + piece + SEG_B + box_off) = x1;
+        if (a.split) {
+            *reinterpret_cast<float4*>(a.pb + piece + 2 * SEG_B + box_off) = tf32_lo4(x0);
+            *reinterpret_cast<float4*>(a.pb + piece + 3 * SEG_B + box_off) = tf32_lo4(x1);
+        }
+    }
+}
+
+template <bool UPDATE, int ST_BN, int ST_STAGES, int ST_NSLOT, bool PACK, bool SPLIT>
 __global__ void __launch_bounds__(ST_THREADS, 1)
 k_tc_stats(const __grid_constant__ CUtensorMap tmVP, const __grid_constant__ CUtensorMap tmVN,
            const __grid_constant__ CUtensorMap tmHP, const __grid_constant__ CUtensorMap tmHN,
            const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWm, StatsArgs a) {
+    static_assert(!SPLIT || PACK, "the exact mode reads packed operands");
+    static_assert(!PACK || ST_BN == 128, "operands are packed for 128-column tiles");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int ST_SEG_B = st_seg_b<ST_BN>();
-    constexpr int ST_STAGE_BYTES = st_stage_bytes<ST_BN>();
+    constexpr int ST_STAGE_BYTES = st_stage_bytes<ST_BN, SPLIT>();
     constexpr int ST_SLICES = ST_BN / 32;                      // 32-column slices of W / W_m per tile
     static_assert(ST_STAGES <= 4 && ST_NSLOT <= 4 && (ST_NSLOT & (ST_NSLOT - 1)) == 0, "ring sizes");
     uint8_t* ops = smem;                                       // operand ring
@@ -90,32 +166,56 @@ k_tc_stats(const __grid_constant__ CUtensorMap tmVP, const __grid_constant__ CUt
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // late_wait: the predecessor is k_colstats, which fires its trigger only after ITS predecessors have
-    // completed and touches nothing this kernel reads or writes: run concurrently with it and restore
-    // the completion chain with a wait at the very end.
-    if (!a.late_wait) pdl_wait();
+    // late_wait (TMA-operand variant): the predecessor is k_colstats, which fires its trigger only after ITS
+    // predecessors have completed and touches nothing this kernel reads or writes: run concurrently with it and
+    // restore the completion chain with a wait at the very end.
+    // PACK variants: the predecessors are k_colstats (same property) and k_pack_ops, whose output only the operand
+    // path reads: the weight stream starts at once, the operand producer and the issuer wait for the pack kernel.
+    if (!PACK && !a.late_wait) pdl_wait();
 
     if (warp == 0) {
         // ===================== operand producer =====================
         if (a.dbg != 1 && elect_one()) {
             int stage = 0; uint32_t phase = 0;
+            bool ext = false;
+            if (PACK) {
+                pdl_wait();
+                ext = SPLIT && __ldcg(a.flags) == a.gen;
+            }
             for (int t = t_beg; t < t_end; t += t_step) {
-                const int m0 = (t / a.n_tiles) * ST_BM, n0 = (t % a.n_tiles) * ST_BN;
-                for (int kc = 0; kc < a.k_chunks; ++kc) {
+                const int mt = t / a.n_tiles, nt = t % a.n_tiles;
+                const int m0 = mt * ST_BM, n0 = nt * ST_BN;
+                const int n_chunks = a.k_chunks * (ext ? 2 : 1);
+                for (int c = 0; c < n_chunks; ++c) {
+                    const int kc = c % a.k_chunks;
                     const int b0 = kc * ST_KC;
                     uint8_t* s0 = ops + stage * ST_STAGE_BYTES;
                     mbar_wait(&ops_empty[stage], phase ^ 1);
-                    mbar_expect_tx(&ops_full[stage], ST_STAGE_BYTES);
+                    if (PACK) {
+                        const size_t pa_off = ((size_t)mt * a.k_chunks + kc) * (2 * ST_SEG_A);
+                        const size_t pb_off = ((size_t)nt * a.k_chunks + kc) * ((SPLIT ? 4 : 2) * ST_SEG_B);
+                        if (c < a.k_chunks) {
+                            mbar_expect_tx(&ops_full[stage], ST_STAGE_BYTES);
+                            bulk_load(s0, a.pa + pa_off, 2 * ST_SEG_A, &ops_full[stage]);
+                            bulk_load(s0 + 2 * ST_SEG_A, a.pb + pb_off, (SPLIT ? 4 : 2) * ST_SEG_B, &ops_full[stage]);
+                        } else {          // second round of an inexact v: [v_lo | h]
+                            mbar_expect_tx(&ops_full[stage], 2 * ST_SEG_A + 2 * ST_SEG_B);
+                            bulk_load(s0, a.pa_lo + pa_off, 2 * ST_SEG_A, &ops_full[stage]);
+                            bulk_load(s0 + 2 * ST_SEG_A, a.pb + pb_off, 2 * ST_SEG_B, &ops_full[stage]);
+                        }
+                    } else {
+                        mbar_expect_tx(&ops_full[stage], ST_STAGE_BYTES);
 #pragma unroll
-                    for (int cb = 0; cb < ST_BM / 32; ++cb) {
-                        tma_load_2d(s0 + cb * ST_OP_BOX, &tmVP, m0 + cb * 32, b0, &ops_full[stage]);
-                        tma_load_2d(s0 + ST_SEG_A + cb * ST_OP_BOX, &tmVN, m0 + cb * 32, b0, &ops_full[stage]);
-                    }
+                        for (int cb = 0; cb < ST_BM / 32; ++cb) {
+                            tma_load_2d(s0 + cb * ST_OP_BOX, &tmVP, m0 + cb * 32, b0, &ops_full[stage]);
+                            tma_load_2d(s0 + ST_SEG_A + cb * ST_OP_BOX, &tmVN, m0 + cb * 32, b0, &ops_full[stage]);
+                        }
 #pragma unroll
-                    for (int cb = 0; cb < ST_BN / 32; ++cb) {
-                        tma_load_2d(s0 + 2 * ST_SEG_A + cb * ST_OP_BOX, &tmHP, n0 + cb * 32, b0, &ops_full[stage]);
-                        tma_load_2d(s0 + 2 * ST_SEG_A + ST_SEG_B + cb * ST_OP_BOX, &tmHN, n0 + cb * 32, b0,
-                                    &ops_full[stage]);
+                        for (int cb = 0; cb < ST_BN / 32; ++cb) {
+                            tma_load_2d(s0 + 2 * ST_SEG_A + cb * ST_OP_BOX, &tmHP, n0 + cb * 32, b0, &ops_full[stage]);
+                            tma_load_2d(s0 + 2 * ST_SEG_A + ST_SEG_B + cb * ST_OP_BOX, &tmHN, n0 + cb * 32, b0,
+                                        &ops_full[stage]);
+                        }
                     }
                     if (++stage == ST_STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -127,13 +227,19 @@ k_tc_stats(const __grid_constant__ CUtensorMap tmVP, const __grid_constant__ CUt
             const uint32_t id_pos = idesc_tf32(ST_BM, ST_BN, true, true, false);
             const uint32_t id_neg = idesc_tf32(ST_BM, ST_BN, true, true, true);     // (-A) * B
             int stage = 0; uint32_t phase = 0;
+            bool ext = false;
+            if (PACK) {
+                pdl_wait();
+                ext = SPLIT && __ldcg(a.flags) == a.gen;
+            }
             int seg = 0;
             for (int t = t_beg; t < t_end; t += t_step, ++seg) {
                 const int buf = seg & 1;
                 mbar_wait(&acc_empty[buf], ((seg >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ST_BN);
-                for (int kc = 0; kc < a.k_chunks; ++kc) {
+                const int n_chunks = a.k_chunks * (ext ? 2 : 1);
+                for (int c = 0; c < n_chunks; ++c) {
                     mbar_wait(&ops_full[stage], phase);
                     tc_fence_after();
                     const uint32_t s0 = smem_u32(ops + stage * ST_STAGE_BYTES);
@@ -144,8 +250,16 @@ k_tc_stats(const __grid_constant__ CUtensorMap tmVP, const __grid_constant__ CUt
                         const uint64_t bp = smem_desc(s0 + 2 * ST_SEG_A + g * 1024, ST_OP_BOX, 512, LAYOUT_SW128_BASE32B);
                         const uint64_t bn = smem_desc(s0 + 2 * ST_SEG_A + ST_SEG_B + g * 1024, ST_OP_BOX, 512,
                                                       LAYOUT_SW128_BASE32B);
-                        mma_tf32(d_tmem, ap, bp, id_pos, (kc | g) != 0);
+                        mma_tf32(d_tmem, ap, bp, id_pos, (c | g) != 0);        // (second round: v_lo * h)
                         mma_tf32(d_tmem, an, bn, id_neg, 1u);
+                        if (SPLIT && c < a.k_chunks) {                          // v * h_lo
+                            const uint64_t bpl = smem_desc(s0 + 2 * ST_SEG_A + 2 * ST_SEG_B + g * 1024, ST_OP_BOX, 512,
+                                                           LAYOUT_SW128_BASE32B);
+                            const uint64_t bnl = smem_desc(s0 + 2 * ST_SEG_A + 3 * ST_SEG_B + g * 1024, ST_OP_BOX, 512,
+                                                           LAYOUT_SW128_BASE32B);
+                            mma_tf32(d_tmem, ap, bpl, id_pos, 1u);
+                            mma_tf32(d_tmem, an, bnl, id_neg, 1u);
+                        }
                     }
                     mma_commit(&ops_empty[stage]);
                     if (++stage == ST_STAGES) { stage = 0; phase ^= 1; }
@@ -197,7 +311,7 @@ k_tc_stats(const __grid_constant__ CUtensorMap tmVP, const __grid_constant__ CUt
             if (a.dbg == 5 && hh > 0) { tma_store_wait_read(); mbar_arrive(&io_empty[(hh - 1) & (ST_NSLOT - 1)]); }
             tma_store_wait_all();                     // global writes complete before the kernel ends
         }
-    } else {
+    } else if (warp >= 4 && warp < 4 + ST_EPI_WARPS) {
         // ===================== epilogue =====================
         // Two groups of four warps; group g owns the quarter-tiles g and g+2 of every tile.  Inside a
         // group, warp <-> TMEM lane quadrant, thread <-> tile row.
@@ -266,7 +380,7 @@ k_tc_stats(const __grid_constant__ CUtensorMap tmVP, const __grid_constant__ CUt
         }
     }
 
-    if (a.late_wait) pdl_wait();
+    if (PACK || a.late_wait) pdl_wait();
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {

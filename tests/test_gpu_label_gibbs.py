@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-@pytest.mark.parametrize("prec,tol", [("fp32", 3e-5), ("tf32", 3e-3)])
+@pytest.mark.parametrize("prec,tol", [("fp32", 3e-5), ("tf32", 3e-3), ("tf32x2", 3e-5)])
 @pytest.mark.parametrize("B,K,n", [(96, 32, 50), (7, 32, 0), (300, 20, 9)])
 def test_label_only_matches_oracle_and_generic_path(prec, tol, B, K, n):
     import multimodal_idbn_b200 as M
