@@ -322,6 +322,73 @@ def gibbs_conditional_step(st: RBMState, v, v_known, km, sample_h=False, sample_
     return v_next * (1 - km) + v_known * km, v_prob
 
 
+def backward_sample(st: RBMState, h: torch.Tensor, fld: RandomField, row0: int = 0) -> torch.Tensor:
+    """``RBM.backward_sample`` (rbm.py:153-156).  Draws: 0 = U[B,V], 1 = categorical."""
+    B = h.shape[0]
+    p = visible_probs(st, h)
+    ucat = [_t(fld.cat_uniform(1, B, g, row0), p) for g in range(len(st.groups))]
+    return sample_visible(st, p, _t(fld.uniform(0, B, st.V, row0), p), ucat)
+
+
+def gibbs_step(st: RBMState, v: torch.Tensor, sample_h: bool = True, sample_v: bool = True,
+               fld: RandomField = None, row0: int = 0):
+    """``RBM.gibbs_step`` (rbm.py:158-178): returns (v_next, v_prob, h, h_prob).
+    Draws: 0 = U[B,H], 1 = U[B,V], 2 = categorical."""
+    B = v.shape[0]
+    h_prob = hidden_probs(st, v)
+    h = (h_prob > _t(fld.uniform(0, B, st.H, row0), v)).to(v.dtype) if sample_h else h_prob
+    v_prob = visible_probs(st, h)
+    if sample_v:
+        ucat = [_t(fld.cat_uniform(2, B, g, row0), v) for g in range(len(st.groups))]
+        v_next = sample_visible(st, v_prob, _t(fld.uniform(1, B, st.V, row0), v), ucat)
+    else:
+        v_next = v_prob
+    return v_next, v_prob, h, h_prob
+
+
+def conditional_gibbs_annealed(st: RBMState, v_known, km, n_steps=40, T0=2.5, T1=1.0, sample_h_until=20,
+                               sample_v_every=0, final_meanfield=True, fld: RandomField = None, row0: int = 0):
+    """``RBM.conditional_gibbs_annealed`` (rbm.py:240-298).  Draws: 0 = U[B,V] init; step t: 1+3t = U[B,H]
+    while t < min(n, sample_h_until); 2+3t = U[B,V] and 3+3t = categorical on the steps that sample v."""
+    B = v_known.shape[0]
+    n = int(n_steps)
+    v = v_known * km + (1 - km) * _t(fld.uniform(0, B, st.V, row0), v_known)
+    hot = int(max(0, min(n, sample_h_until)))
+    for t in range(n):
+        Tt = lin_schedule(t, n, T0, T1)
+        if (n - t) <= 3:
+            Tt = min(0.9, Tt)
+        h_prob = hidden_probs(st, v, T=Tt)
+        h = (h_prob > _t(fld.uniform(1 + 3 * t, B, st.H, row0), v)).to(v.dtype) if t < hot else h_prob
+        v_prob = visible_probs(st, h, T=Tt)
+        if t < hot and sample_v_every > 0 and t % sample_v_every == 0:
+            ucat = [_t(fld.cat_uniform(3 + 3 * t, B, g, row0), v) for g in range(len(st.groups))]
+            v_new = sample_visible(st, v_prob, _t(fld.uniform(2 + 3 * t, B, st.V, row0), v), ucat)
+        else:
+            v_new = v_prob
+        v = v_new * (1 - km) + v_known * km
+    if final_meanfield:
+        v = visible_probs(st, hidden_probs(st, v, T=1.0), T=1.0) * (1 - km) + v_known * km
+    return v
+
+
+def finetune_last_layer(layers: Sequence[RBMState], batches: Sequence[torch.Tensor], epochs: int, lr_scale: float,
+                        k: int, flds: Sequence[RandomField]) -> None:
+    """``iMDBN.finetune_image_last_layer`` (imdbn.py:344-384): the lower layers only feed forward, the last layer
+    trains with its learning rate scaled (restored afterwards); one random field per ``train_epoch`` call."""
+    last = layers[-1]
+    old = last.lr
+    last.lr = max(1e-8, old * float(lr_scale))
+    it = iter(flds)
+    for ep in range(int(epochs)):
+        for x in batches:
+            v = x.reshape(x.shape[0], -1).float()
+            for st in layers[:-1]:
+                v = hidden_probs(st, v)
+            cd_train(last, v, ep, k, next(it))
+    last.lr = old
+
+
 def cd_clamped_statistics(st: RBMState, v_known, km, k=1, cond_init_steps=50, sample_h=True,
                           sample_v=False, reclamp_negative=True, use_noisy_init=True,
                           fld: RandomField = None, row0: int = 0):

@@ -69,13 +69,14 @@ class DrawPlan:
     def __init__(self):
         self.q = []
 
-    def push(self, kind, fld, draw, group=0):
-        self.q.append((kind, fld, draw, group))
+    def push(self, kind, fld, draw, group=0, row0=0):
+        self.q.append((kind, fld, draw, group, row0))
 
     def pop(self, kind):
         assert self.q, f"reference drew an unplanned '{kind}'"
-        k, fld, draw, group = self.q.pop(0)
+        k, fld, draw, group, row0 = self.q.pop(0)
         assert k == kind, f"plan says '{k}' but the reference drew '{kind}'"
+        self.row0 = row0
         return fld, draw, group
 
     def done(self):
@@ -92,7 +93,7 @@ class _Categorical:
 
     def sample(self):
         fld, draw, group = PLAN.pop("cat")
-        u = torch.from_numpy(fld.cat_uniform(draw, self.probs.shape[0], group))
+        u = torch.from_numpy(fld.cat_uniform(draw, self.probs.shape[0], group, PLAN.row0))
         return O.categorical_index(self.probs, u)
 
 
@@ -106,11 +107,11 @@ class _TorchProxy:
 
     def rand_like(self, x):
         fld, draw, _ = PLAN.pop("u")
-        return torch.from_numpy(fld.uniform(draw, x.shape[0], x.shape[1])).to(x.dtype)
+        return torch.from_numpy(fld.uniform(draw, x.shape[0], x.shape[1], PLAN.row0)).to(x.dtype)
 
     def randn_like(self, x):
         fld, draw, _ = PLAN.pop("n")
-        return torch.from_numpy(fld.normal(draw, x.shape[0], x.shape[1])).to(x.dtype)
+        return torch.from_numpy(fld.normal(draw, x.shape[0], x.shape[1], PLAN.row0)).to(x.dtype)
 
 
 ref_rbm_mod.torch = _TorchProxy(torch)
@@ -590,6 +591,163 @@ def case_bimodal():
     save("bimodal", **out)
 
 
+def case_rbm_extra():
+    """backward_sample (rbm.py:153-156), gibbs_step (:158-178), conditional_gibbs_annealed (:240-298)."""
+    r = make_rbm(26, 12, 201, groups=[(20, 26)])
+    B, Dz = 6, 20
+    h = unit(B, 12, 202)
+    v0 = torch.cat([unit(B, Dz, 203), onehot(B, 6, 204)], dim=1)
+    out = dict(params_of(r, "in_"), groups=np.array(r.softmax_groups), h=h, v0=v0, seed=SEED)
+    # backward_sample: U[B,V] (draw 0), categorical (draw 1)
+    fld = RandomField(SEED, 0)
+    PLAN.push("u", fld, 0); PLAN.push("cat", fld, 1, 0)
+    out["backward_sample"] = r.backward_sample(h)
+    PLAN.done()
+    # gibbs_step: U[B,H] (0), U[B,V] (1), categorical (2)
+    for i, (sh, sv) in enumerate([(True, True), (True, False), (False, True), (False, False)]):
+        fld = RandomField(SEED, 1 + i)
+        if sh:
+            PLAN.push("u", fld, 0)
+        if sv:
+            PLAN.push("u", fld, 1); PLAN.push("cat", fld, 2, 0)
+        vn, vp, hh, hp = r.gibbs_step(v0, sample_h=sh, sample_v=sv)
+        PLAN.done()
+        out[f"gs{i}_v_next"] = vn; out[f"gs{i}_v_prob"] = vp; out[f"gs{i}_h"] = hh; out[f"gs{i}_h_prob"] = hp
+    out["gs_cfg"] = np.array([(1, 1), (1, 0), (0, 1), (0, 0)])
+    # conditional_gibbs_annealed: U[B,V] init (0); step t: U[B,H] (1+3t) while t < hot; U[B,V] (2+3t) and
+    # categorical (3+3t) when v is sampled
+    vk = torch.zeros(B, 26); km = torch.zeros(B, 26)
+    vk[:, :Dz] = unit(B, Dz, 205); km[:, :Dz] = 1.0
+    cfgs = [(8, 2.5, 1.0, 4, 2, True), (6, 2.0, 1.0, 6, 0, False), (5, 2.5, 1.0, 0, 0, True), (4, 3.0, 0.8, 2, 1, True)]
+    for i, (n, T0, T1, until, every, final) in enumerate(cfgs):
+        fld = RandomField(SEED, 10 + i)
+        PLAN.push("u", fld, 0)
+        hot = max(0, min(n, until))
+        for t in range(n):
+            if t < hot:
+                PLAN.push("u", fld, 1 + 3 * t)
+                if every > 0 and t % every == 0:
+                    PLAN.push("u", fld, 2 + 3 * t); PLAN.push("cat", fld, 3 + 3 * t, 0)
+        out[f"cga{i}"] = r.conditional_gibbs_annealed(vk, km, n_steps=n, T0=T0, T1=T1, sample_h_until=until,
+                                                       sample_v_every=every, final_meanfield=final)
+        PLAN.done()
+    out["cga_cfg"] = np.array([[c[0], c[1], c[2], c[3], c[4], float(c[5])] for c in cfgs])
+    out["v_known"] = vk; out["km"] = km
+    save("rbm_extra", **out)
+
+
+class _Recorder:
+    """Stand-in for a wandb run: keeps what the reference logs (scalars / dicts only)."""
+
+    def __init__(self):
+        self.logs = []
+
+    def log(self, d, *a, **k):
+        self.logs.append(d)
+
+
+def _small_imdbn(seed0, N=24, D=40, K=4, wandb_run=None):
+    x = binary(N, D, seed0 + 1).view(N, 1, 5, 8)
+    y = onehot(N, K, seed0 + 2)
+    dl = _loader(x, y, 8)
+    m = ref_imdbn_mod.iMDBN([D, 20, 10], 8, params=dict(PARAMS), dataloader=dl, val_loader=dl,
+                            device=torch.device("cpu"), num_labels=K, wandb_run=wandb_run)
+    _seed_idbn(m.image_idbn, seed0 + 10)
+    jr = m.joint_rbm
+    g = torch.Generator().manual_seed(seed0 + 20)
+    with torch.no_grad():
+        jr.W.copy_(torch.randn(jr.num_visible, jr.num_hidden, generator=g) * 0.8)
+        jr.hid_bias.copy_(torch.randn(jr.num_hidden, generator=g) * 0.2)
+    return m, x, y
+
+
+def case_finetune():
+    """iMDBN.finetune_image_last_layer (imdbn.py:344-384): 2 epochs x 3 batches, lr scaled by 0.3, CD-2."""
+    m, x, y = _small_imdbn(300)
+    out = dict(x=x, y=y, seed=SEED, batch=8)
+    for i, r in enumerate(m.image_idbn.layers):
+        out.update(params_of(r, f"in_l{i}_"))
+    last = m.image_idbn.layers[-1]
+    lr0 = float(last.lr)
+    stream = 0
+    for ep in range(2):
+        for b in range(3):
+            plan_cd(RandomField(SEED + 1, stream), 2, 0); stream += 1
+    m.finetune_image_last_layer(epochs=2, lr_scale=0.3, cd_k=2)
+    PLAN.done()
+    assert float(last.lr) == lr0
+    for i, r in enumerate(m.image_idbn.layers):
+        out.update(params_of(r, f"out_l{i}_"))
+    out["lr_after"] = float(last.lr)
+    save("finetune", **out)
+
+
+def case_panel():
+    """run_and_log_cross_fixed_case (conditional_steps.py:364-387), run_and_log_cross_panel (:474-555) and
+    run_and_log_z_mismatch_check (:557-646) with the plotting stubbed and a recording wandb run.
+    Draw convention of the batched drop-in: ONE stream per call of the joint RBM, sample i = row i."""
+    rec = _Recorder()
+    # plotting is out of scope: stub the three matplotlib / wandb.Image touch points of the module
+    ref_steps_mod.log_cross_case = lambda *a, **k: None
+    ref_steps_mod._plot_steps_hist_with_nc = lambda *a, **k: None
+    ref_steps_mod.wandb = types.SimpleNamespace(Image=lambda fig: None)
+    ref_steps_mod.plt = types.SimpleNamespace(close=lambda fig: None)
+    m, x, y = _small_imdbn(400, wandb_run=rec)
+    jr = m.joint_rbm
+    m.init_joint_bias_from_data(n_batches=3)
+    out = dict(x=x, y=y, K=4)
+    for i, r in enumerate(m.image_idbn.layers):
+        out.update(params_of(r, f"l{i}_"))
+    out.update(params_of(jr, "joint_"))
+    out["z_class_mean"] = m.z_class_mean.clone()
+    JSEED = SEED + 400
+    kw = dict(max_steps=10)
+    # ---- fixed case: one sample (the first of class 2 in the first batch that has one)
+    PLAN.push("u", RandomField(JSEED, 0), 0)
+    a, b = ref_steps_mod.run_and_log_cross_fixed_case(m, epoch=0, target_label=2, **kw)
+    PLAN.done()
+    out["fixed_img"] = m._fixed_val_case[0]; out["fixed_lbl"] = m._fixed_val_case[1]
+    out["fixed_a_steps"] = a["steps_to_converge"]; out["fixed_a_p_top1"] = np.array(a["p_top1"])
+    out["fixed_a_l1"] = np.array(a["l1"]); out["fixed_a_top1_idx"] = np.array(a["top1_idx"])
+    out["fixed_b_steps"] = b["steps_to_converge"]; out["fixed_b_z_l2"] = np.array(b["z_l2"])
+    out["fixed_b_image_mse"] = np.array(b["image_mse"])
+    # ---- panel: per_class = 2
+    imgs, lbls = ref_steps_mod.build_or_get_fixed_val_panel(m, per_class=2)
+    n = imgs.size(0)
+    for i in range(n):
+        PLAN.push("u", RandomField(JSEED, 1), 0, row0=i)
+    p = ref_steps_mod.run_and_log_cross_panel(m, epoch=0, per_class=2, **kw)
+    PLAN.done()
+    out["panel_imgs"] = imgs; out["panel_lbls"] = lbls
+    out["panel_i2t_steps"] = np.array(p["img2txt"]["steps"]); out["panel_t2i_steps"] = np.array(p["txt2img"]["steps"])
+    st = p["img2txt"]["stats"]
+    out["panel_i2t_stats"] = np.array([st["n_total"], st["n_converged"], st["frac_converged"],
+                                       -1.0 if st["mean"] is None else st["mean"],
+                                       -1.0 if st["p50"] is None else st["p50"],
+                                       -1.0 if st["p95"] is None else st["p95"]], dtype=np.float64)
+    st = p["txt2img"]["stats"]
+    out["panel_t2i_stats"] = np.array([st["n_total"], st["n_converged"], st["frac_converged"],
+                                       -1.0 if st["mean"] is None else st["mean"],
+                                       -1.0 if st["p50"] is None else st["p50"],
+                                       -1.0 if st["p95"] is None else st["p95"]], dtype=np.float64)
+    out["panel_p1_mean"] = p["img2txt"]["p1_mean"]; out["panel_gap_mean"] = p["img2txt"]["gap_mean"]
+    out["panel_best_mse_mean"] = p["txt2img"]["best_mse_mean"]
+    summ = [d for d in rec.logs if any(k.endswith("/summary") for k in d)]
+    assert len(summ) == 1
+    # ---- z mismatch check on the first validation batch (8 samples), 6 steps
+    rec.logs.clear()
+    for i in range(8):
+        PLAN.push("u", RandomField(JSEED, 2), 0, row0=i)
+    ref_steps_mod.run_and_log_z_mismatch_check(m, epoch=0, max_steps=6)
+    PLAN.done()
+    zl = {k.split("/")[-1]: v for d in rec.logs for k, v in d.items() if k.startswith("zcheck/")}
+    out["z_img_stats"] = np.array([zl["z_img_stats"][k] for k in ("mean", "std", "q10", "q90")])
+    out["z_y_stats"] = np.array([zl["z_y_stats"][k] for k in ("mean", "std", "q10", "q90")])
+    out["z_cosine_mean"] = zl["cosine_mean"]
+    out["seed_joint"] = JSEED
+    save("panel", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)  # fixtures should not depend on the thread count of this machine
     case_passes()
@@ -601,3 +759,6 @@ if __name__ == "__main__":
     case_imdbn()
     case_bimodal()
     case_energy()
+    case_rbm_extra()
+    case_finetune()
+    case_panel()

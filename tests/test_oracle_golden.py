@@ -298,3 +298,38 @@ def test_energy_diagnostics():
             np.testing.assert_allclose(tr[key], g[f"t{i}_{key}"], rtol=1e-5, atol=1e-6, err_msg=key)
         for key in TRACE_SCALARS:
             np.testing.assert_allclose(tr[key], g[f"t{i}_{key}"], rtol=1e-5, atol=1e-6, err_msg=key)
+
+
+def test_rbm_extra_backward_sample_gibbs_step_annealed():
+    """backward_sample, gibbs_step and conditional_gibbs_annealed (rbm.py:153-178, 240-298) against the reference."""
+    g = load_golden("rbm_extra")
+    st = state_from(g, "in_", g["groups"])
+    seed = int(g["seed"])
+    h, v0 = T(g["h"]), T(g["v0"])
+    assert torch.equal(O.backward_sample(st, h, RandomField(seed, 0)), T(g["backward_sample"]))
+    for i, (sh, sv) in enumerate(g["gs_cfg"]):
+        vn, vp, hh, hp = O.gibbs_step(st, v0, bool(sh), bool(sv), RandomField(seed, 1 + i))
+        torch.testing.assert_close(vn, T(g[f"gs{i}_v_next"]), **TOL)
+        torch.testing.assert_close(vp, T(g[f"gs{i}_v_prob"]), **TOL)
+        torch.testing.assert_close(hh, T(g[f"gs{i}_h"]), **TOL)
+        torch.testing.assert_close(hp, T(g[f"gs{i}_h_prob"]), **TOL)
+    vk, km = T(g["v_known"]), T(g["km"])
+    for i, (n, T0, T1, until, every, final) in enumerate(g["cga_cfg"]):
+        out = O.conditional_gibbs_annealed(st, vk, km, int(n), float(T0), float(T1), int(until), int(every),
+                                           bool(final), RandomField(seed, 10 + i))
+        torch.testing.assert_close(out, T(g[f"cga{i}"]), **TOL)
+
+
+def test_finetune_image_last_layer():
+    """iMDBN.finetune_image_last_layer (imdbn.py:344-384): only the last image layer moves, lr restored."""
+    g = load_golden("finetune")
+    layers = idbn_layers(g, "in_")
+    x = T(g["x"]).reshape(g["x"].shape[0], -1)
+    seed, bs = int(g["seed"]), int(g["batch"])
+    batches = [x[b0:b0 + bs] for b0 in range(0, x.shape[0], bs)]
+    lr0 = layers[-1].lr
+    O.finetune_last_layer(layers, batches, 2, 0.3, 2, [RandomField(seed + 1, s) for s in range(2 * len(batches))])
+    assert layers[-1].lr == lr0
+    for i, st in enumerate(layers):
+        check_params(st, g, f"out_l{i}_")
+    torch.testing.assert_close(layers[0].W, T(g["in_l0_W"]))
