@@ -92,7 +92,8 @@ int64_t imdbn_launch_count(imdbn_ctx* ctx);
  * While enabled, the GEMM-shaped kernels and the chain kernel are bracketed by CUDA events recorded
  * on the launching stream.  imdbn_profile_read synchronises those events and returns the summed
  * duration (ms) and launch count of the kernels of `kind` that ran on an RBM of shape (V, H). */
-enum { IMDBN_KERNEL_UP = 0, IMDBN_KERNEL_DOWN = 1, IMDBN_KERNEL_STATS = 2, IMDBN_KERNEL_CHAIN = 3 };
+enum { IMDBN_KERNEL_UP = 0, IMDBN_KERNEL_DOWN = 1, IMDBN_KERNEL_STATS = 2, IMDBN_KERNEL_CHAIN = 3,
+       IMDBN_KERNEL_PACK = 4 /* operand packing pass in front of the small-batch statistics kernel */ };
 int imdbn_profile_enable(imdbn_ctx* ctx, int enable);
 int imdbn_profile_read(imdbn_ctx* ctx, int kind, int V, int H, double* ms_sum, int64_t* count);
 

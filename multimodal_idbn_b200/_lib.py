@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(_HERE, "libimdbn_b200.so")
 MAX_GROUPS = 4
 PREC_FP32, PREC_TF32, PREC_TF32X2 = 0, 1, 2
 CHAIN_NOISY_MF, CHAIN_COND_GIBBS = 0, 1
-KERNEL_UP, KERNEL_DOWN, KERNEL_STATS, KERNEL_CHAIN = 0, 1, 2, 3
+KERNEL_UP, KERNEL_DOWN, KERNEL_STATS, KERNEL_CHAIN, KERNEL_PACK = 0, 1, 2, 3, 4
 
 c_float_p = C.POINTER(C.c_float)
 
@@ -234,19 +234,20 @@ _partitions = {}
 
 def sm_partition(device_index: int, small_sms: int):
     """``(stream_big, stream_small, n_big, n_small)`` -- raw handles of two streams on disjoint SM sets (CUDA green
-    contexts, ``imdbn_sm_partition``), or None when the driver cannot provide them.  One partition per device."""
+    contexts, ``imdbn_sm_partition``), or None when the driver cannot provide them.  One partition per (device, size)."""
     # Nsight Compute cannot profile kernels of green contexts ("Failed to prepare kernel for profiling"): profiling
     # runs use IMDBN_NO_PARTITION=1 (layer pipelining then falls back to an ordinary side stream)
     if os.environ.get("IMDBN_NO_PARTITION") or os.environ.get("CUDA_INJECTION64_PATH"):
         return None
-    if device_index not in _partitions:
+    key = (device_index, int(small_sms))
+    if key not in _partitions:
         lib = load_library()
         big, small = C.c_void_p(), C.c_void_p()
         nb, ns = C.c_int(), C.c_int()
         rc = lib.imdbn_sm_partition(int(device_index), int(small_sms), C.byref(big), C.byref(small), C.byref(nb),
                                     C.byref(ns))
-        _partitions[device_index] = (big.value, small.value, nb.value, ns.value) if rc == 0 and big.value else None
-    return _partitions[device_index]
+        _partitions[key] = (big.value, small.value, nb.value, ns.value) if rc == 0 and big.value else None
+    return _partitions[key]
 
 
 def context_for_stream(device_index: int, stream_handle: int) -> "Context":

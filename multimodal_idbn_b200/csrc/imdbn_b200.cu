@@ -97,9 +97,9 @@ int gemm_down(imdbn_ctx* ctx, const imdbn_rbm* r, const float* h, int B, const P
 int gemm_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* vp, const float* hp,
                const float* vn, const float* hn, int B, float* dS_out, const imdbn_update* upd,
                cudaStream_t st) {
-    ProfScope prof(ctx, IMDBN_KERNEL_STATS, r->V, r->H, st);
     if (uses_tc(ctx) && tc_stats_supported(ctx, r, B))
-        return tc_gemm_stats(ctx, r, vp, hp, vn, hn, B, dS_out, upd, st);
+        return tc_gemm_stats(ctx, r, vp, hp, vn, hn, B, dS_out, upd, st);     // (profiles its two kernels itself)
+    ProfScope prof(ctx, IMDBN_KERNEL_STATS, r->V, r->H, st);
     GemmArgs g{};
     g.A = vp; g.sAm = 1; g.sAk = r->V;
     g.B = hp; g.sBk = r->H; g.sBn = 1;
@@ -498,6 +498,8 @@ static bool cd_small_eligible(const imdbn_ctx* ctx, const imdbn_rbm* r, const fl
     return ctx->num_sms >= 8;
 }
 
+constexpr int CDS_FALLBACK = -1000;       // cd_small could not launch cooperatively: use the multi-launch path
+
 static int cd_small(imdbn_ctx* ctx, const imdbn_rbm* r, const float* data, int B, int k,
                     const imdbn_update* upd, const imdbn_rng* rng, float* loss_out, cudaStream_t st,
                     const FwdTail* tail) {
@@ -539,7 +541,24 @@ static int cd_small(imdbn_ctx* ctx, const imdbn_rbm* r, const float* data, int B
         attr_set = true;
     }
     ProfScope prof(ctx, IMDBN_KERNEL_STATS, V, H, st);
-    IMDBN_CUDA(ctx, launch_pdl(k_cd_small, dim3(G), dim3(CDS_THREADS), (size_t)CDS_SMEM_BYTES, st, a));
+    {
+        // The kernel synchronises its CTAs with grid barriers: a COOPERATIVE launch makes the driver guarantee that
+        // all G CTAs are resident together (kernels of other streams holding SMs delay the launch instead of
+        // dead-locking a partially resident grid); if the grid can never fit (SMs limited by the context, MPS)
+        // the launch fails and the caller takes the multi-launch path.
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(G); cfg.blockDim = dim3(CDS_THREADS); cfg.dynamicSmemBytes = (size_t)CDS_SMEM_BYTES; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, k_cd_small, a);
+        if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources || e == cudaErrorNotSupported) {
+            (void)cudaGetLastError();
+            return CDS_FALLBACK;
+        }
+        IMDBN_CUDA(ctx, e);
+    }
     IMDBN_CHECK_LAUNCH(ctx, "k_cd_small");
     if (trace_on) {
         static int calls = 0;
@@ -561,8 +580,10 @@ int cd_core(imdbn_ctx* ctx, const imdbn_rbm* r, const float* data, int B, int k,
     int rc = check_rbm(ctx, r, stats_out == nullptr);
     if (rc) return rc;
     IMDBN_ARG(ctx, data && B > 0 && k >= 1 && rng);
-    if (!stats_out && upd && cd_small_eligible(ctx, r, data, B, tail))
-        return cd_small(ctx, r, data, B, k, upd, rng, loss_out, st, tail);
+    if (!stats_out && upd && cd_small_eligible(ctx, r, data, B, tail)) {
+        rc = cd_small(ctx, r, data, B, k, upd, rng, loss_out, st, tail);
+        if (rc != CDS_FALLBACK) return rc;
+    }
     const int V = r->V, H = r->H;
     const PassPlan pu = plan_pass(ctx, r, B, true), pd = plan_pass(ctx, r, B, false);
     const size_t nBH = (size_t)B * H, nBV = (size_t)B * V;

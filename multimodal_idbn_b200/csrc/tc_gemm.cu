@@ -639,7 +639,10 @@ int tc_gemm_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* vp, const flo
         if (pk.gen == 0) pk.gen = ++ctx->pack_gen;                 // 0 = the memset value, never a valid generation
         pk.after_colstats = after_colstats ? 1 : 0;
         const int n4 = (a.m_tiles + a.n_tiles) * 32;
-        IMDBN_CUDA(ctx, launch_pdl(k_pack_ops, dim3((n4 + 255) / 256, a.k_chunks * ST_KC), dim3(256), 0, st, pk));
+        {
+            ProfScope prof(ctx, IMDBN_KERNEL_PACK, r->V, r->H, st);
+            IMDBN_CUDA(ctx, launch_pdl(k_pack_ops, dim3((n4 + 255) / 256, a.k_chunks * ST_KC), dim3(256), 0, st, pk));
+        }
         IMDBN_CHECK_LAUNCH(ctx, "k_pack_ops");
         a.pa = pk.pa; a.pa_lo = pk.pa_lo; a.pb = pk.pb; a.flags = pk.flags; a.gen = pk.gen;
     }
@@ -654,6 +657,7 @@ int tc_gemm_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* vp, const flo
     };
     static bool set[6] = {false, false, false, false, false, false};
     cudaError_t e;
+    ProfScope prof(ctx, IMDBN_KERNEL_STATS, r->V, r->H, st);
     if (split)
         e = dS_out ? launch(k_tc_stats<false, 128, 2, 4, true, true>, st_smem<128, 2, 4, true>(), set[4])
                    : launch(k_tc_stats<true, 128, 2, 4, true, true>, st_smem<128, 2, 4, true>(), set[5]);
@@ -670,8 +674,9 @@ int tc_gemm_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* vp, const flo
 
 // ---- SM partition (CUDA green contexts): two streams whose kernels run on disjoint sets of SMs ---------------
 namespace {
-struct SmPartition { bool tried = false; bool ok = false; CUstream big = nullptr, small_ = nullptr; int n_big = 0, n_small = 0; };
-SmPartition g_partitions[16];
+struct SmPartition { bool tried = false; bool ok = false; CUstream big = nullptr, small_ = nullptr; int n_big = 0, n_small = 0; int want = 0; };
+constexpr int kPartitionsPerDevice = 6;     // distinct reserve sizes a process may ask for
+SmPartition g_partitions[16][kPartitionsPerDevice];
 
 template <typename Fn>
 bool drv(const char* name, Fn* out) {
@@ -686,8 +691,15 @@ bool drv(const char* name, Fn* out) {
 
 int sm_partition(int device, int small_sms, void** stream_big, void** stream_small, int* n_big, int* n_small) {
     if (device < 0 || device >= 16 || !stream_big || !stream_small || small_sms < 8) return -1;
-    SmPartition& P = g_partitions[device];
+    SmPartition* slot = nullptr;
+    for (int i = 0; i < kPartitionsPerDevice && !slot; ++i)
+        if (g_partitions[device][i].tried && g_partitions[device][i].want == small_sms) slot = &g_partitions[device][i];
+    for (int i = 0; i < kPartitionsPerDevice && !slot; ++i)
+        if (!g_partitions[device][i].tried) slot = &g_partitions[device][i];
+    if (!slot) return -10;                  // too many different partition sizes on this device
+    SmPartition& P = *slot;
     if (!P.tried) {
+        P.want = small_sms;
         P.tried = true;
         typedef CUresult (*FGetDev)(CUdevice*, int);
         typedef CUresult (*FGetRes)(CUdevice, CUdevResource*, CUdevResourceType);

@@ -4,7 +4,8 @@ Training (``RBM.train_epoch`` / ``train_epoch_clamped``): every rank holds the f
 momenta, receives its own shard of the minibatch, computes the local CD statistics
 ``[dS | dh | dv | sum pos_h | squared error]`` with the same kernels, and ONE sum all-reduce (NCCL
 over NVLink / NVSwitch) per update makes them global; every rank then applies the identical update,
-so replicas stay bit-identical.  Random numbers are addressed by the GLOBAL row index, so the result
+so replicas stay bit-identical.  Identical STARTING parameters are established by the first update after
+``enable()``: it broadcasts rank 0's W, biases and momenta (``RBM._dp_sync_params``).  Random numbers are addressed by the GLOBAL row index, so the result
 does not depend on the number of ranks (up to the summation order of the all-reduce).
 
 With NCCL ranks on one NVLink / NVSwitch box the exchange does not go through NCCL at all (``p2p``

@@ -244,6 +244,17 @@ class iDBN:
         st = d.get("_fused")
         key = (B, Bn, dev, s_caller, piped, reserve, n, id(self.layers[-1]))
         if st is None or st["key"] != key:
+            if st is not None:
+                # the old rings / loss ring may still be read and written by the previous steps' kernels on the side
+                # or partition streams: join them into the caller's stream, on which the caching allocator orders the
+                # re-use of the storage we are about to drop
+                self.sync()
+                for s_old in st.get("streams") or ():
+                    for ring in st["rings"]:
+                        for t in ring:
+                            t.record_stream(s_old)
+                    if st.get("loss_ring") is not None:
+                        st["loss_ring"].record_stream(s_old)
             ctx_c, s_caller = L.context_for(v)
             rings = [[torch.empty(B + (Bn if l == 0 else 0), r.num_hidden, device=dev, dtype=torch.float32)
                       for l, r in enumerate(self.layers)] for _ in range(2)]
@@ -270,6 +281,8 @@ class iDBN:
                 st["streams"] = [side]
                 st["early"] = 0
                 ctx_c.set_sm_limit(max(8, n_sms - reserve) if reserve > 0 else 0)
+                if reserve > 0:              # the side stream's persistent grids stay inside the SMs left to them
+                    st["ctx1"].set_sm_limit(reserve)
             else:
                 ctx_c.set_sm_limit(0)
             self._fused = st
@@ -302,13 +315,20 @@ class iDBN:
             # epoch-dependent hyper-parameters); per step only the call number of the random field moves
             rd = rbm.__dict__
             wm = rd.get("W_m")
-            key = (rbm._parameters["W"].data_ptr(), wm.data_ptr() if wm is not None else 0, epoch, rd["lr"],
-                   rd["sparsity"])
+            hbm, vbm, ps = rd.get("hb_m"), rd.get("vb_m"), rbm._parameters
+            key = (ps["W"].data_ptr(), ps["hid_bias"].data_ptr(), ps["vis_bias"].data_ptr(),
+                   wm.data_ptr() if wm is not None else 0, hbm.data_ptr() if hbm is not None else 0,
+                   vbm.data_ptr() if vbm is not None else 0, epoch, rd["lr"], rd["sparsity"], rd["momentum"],
+                   rd["final_momentum"], rd["weight_decay"], rd["sparsity_factor"], rd["dynamic_lr"],
+                   tuple(map(tuple, rd.get("softmax_groups") or ())))
             if ident[l] != key:
                 lr, mom = rbm._hyper(epoch)
-                st["rbms"][l] = rbm._struct(training=True)
+                st["rbms"][l] = rbm._struct(training=True)          # (may re-home the momenta: rebuild the key after)
                 st["upds"][l] = rbm._update_struct(lr, mom, B, rbm.sparsity)
-                ident[l] = (rbm.W.data_ptr(), rbm.W_m.data_ptr(), epoch, rbm.lr, rbm.sparsity)
+                ident[l] = (rbm.W.data_ptr(), rbm.hid_bias.data_ptr(), rbm.vis_bias.data_ptr(), rbm.W_m.data_ptr(),
+                            rbm.hb_m.data_ptr(), rbm.vb_m.data_ptr(), epoch, rbm.lr, rbm.sparsity, rbm.momentum,
+                            rbm.final_momentum, rbm.weight_decay, rbm.sparsity_factor, rbm.dynamic_lr,
+                            tuple(map(tuple, rbm.softmax_groups or ())))
             if "_rng_seed" not in rd:                    # object un-pickled from a reference checkpoint
                 rngs[l] = rbm._next_rng()
             else:

@@ -214,6 +214,8 @@ class RBM(nn.Module):
         B = data.shape[0]
         lr, mom = self._hyper(epoch)
         dp = _dist.state()
+        if dp is not None:
+            self._dp_sync_params(dp)            # (collective, first call only) rank 0's parameters everywhere
         if dp is not None and dp.p2p:
             self._p2p_setup(dp)                 # (collective, first call only) re-homes W in peer-mapped memory
         rs = self._struct(training=True)
@@ -239,6 +241,18 @@ class RBM(nn.Module):
         self._dp_apply(dp, ctx, rs, stats, upd, loss, st)
 
     # ------------------------------------------------------------------ data parallelism
+    def _dp_sync_params(self, dp) -> None:
+        """Replicated data parallelism needs identical parameters and momenta on every rank, and nothing else
+        establishes that (the constructor draws W from each process's own generator): the first update under a
+        given ``dist.enable()`` broadcasts rank 0's state.  Collective; once per (RBM, dist state)."""
+        if self.__dict__.get("_dp_synced") is dp:
+            return
+        import torch.distributed as td
+        self._sync_buffers()
+        for t in (self.W.data, self.hid_bias.data, self.vis_bias.data, self.W_m, self.hb_m, self.vb_m):
+            td.broadcast(t, src=td.get_global_rank(dp.group, 0) if dp.group is not None else 0, group=dp.group)
+        self._dp_synced = dp
+
     def _p2p_setup(self, dp):
         """Peer-memory data parallelism (dist.py, csrc/dp_update.cuh): the statistics buffer and W live in
         symmetric memory that every rank of the box can load from / store to over NVLink."""
@@ -345,6 +359,7 @@ class RBM(nn.Module):
         ctx, st = self._ctx()
         B = data.shape[0]
         lr, mom = self._hyper(epoch)
+        self._dp_sync_params(dp)
         if dp.p2p:
             self._p2p_setup(dp)
         rs = self._struct(training=True)
@@ -506,6 +521,8 @@ class RBM(nn.Module):
         B = vk.shape[0]
         lr, mom = self._hyper(epoch, aux_lr_mult)
         dp = _dist.state()
+        if dp is not None:
+            self._dp_sync_params(dp)
         if dp is not None and dp.p2p:
             self._p2p_setup(dp)
         rs = self._struct(training=True)
@@ -535,6 +552,7 @@ class RBM(nn.Module):
         state.pop("_stats_buf", None)       # scratch, not model state
         state.pop("_pos_cache", None)
         state.pop("_p2p", None)             # peer-memory handles
+        state.pop("_dp_synced", None)
         return state
 
 
