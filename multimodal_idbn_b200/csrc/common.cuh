@@ -24,6 +24,7 @@ struct Arena {
 
 namespace imdbn {
 struct ProfRec { int kind, V, H; cudaEvent_t a, b; };
+struct ColstatsJob;
 }
 
 struct imdbn_ctx {
@@ -43,6 +44,11 @@ struct imdbn_ctx {
                                          // still in flight writes W (set by cd_core around the passes of one CD-k update)
     bool act_exact = false;              // the activations of the next tensor-core pass are sampled states (0 / 1): exactly
                                          // representable in tf32, the exact mode needs no remainder tile for them
+    const imdbn::ColstatsJob* colstats_job = nullptr;   // set by finish_stats when the next statistics call will pack
+    const uint32_t* act_hint = nullptr;  // the next pass's activations were scanned by the packing pass of this update:
+    uint32_t act_hint_gen = 0;           // act_hint[0], act_hint[1] != act_hint_gen  <=>  exactly representable in tf32
+    const float* pack_scan = nullptr;    // extra matrix the next packing pass scans for exactness ([pack_scan_rows, V])
+    int pack_scan_rows = 0;
     bool stats_after_colstats = false;   // next tc statistics kernel directly follows k_colstats (see tc_stats.cuh)
     uint32_t* pack_flags = nullptr;      // device: [0] = generation of the last statistics call whose v operand was inexact in tf32
     uint32_t pack_gen = 0;
@@ -186,6 +192,22 @@ inline Groups make_groups(const imdbn_rbm* r) {
     }
     return g;
 }
+
+struct BiasArgs {            // apply != 0: update the biases of the block's columns in the same kernel
+    int apply;
+    float* hb; float* hbm; float* vb; float* vbm;
+    float lr, mom, bsz; int sparsity; float sp_target;
+    float n_loss; float* loss_out;
+};
+// Column statistics of a CD update (k_colstats) handed to the tensor-core statistics path, which computes them in
+// its operand-packing pass over the same four matrices (k_pack_colstats) instead of a kernel of their own.
+struct ColstatsJob {
+    const float* ea; const float* eb;      // squared error sum((ea - eb)^2) over [B,V]
+    float* out;                            // [dh (H) | dv (V) | pos_h column sum (H) | squared error (1)]
+    float* sq_part;                        // >= m_tiles + n_tiles floats
+    unsigned int* ticket;
+    BiasArgs ba;
+};
 
 // Stream-K partition of the tensor-core passes (tc_gemm.cu): the flattened (output tile, k-iteration)
 // space of `total` iterations is cut into G contiguous, equally long ranges, one per CTA.  An output

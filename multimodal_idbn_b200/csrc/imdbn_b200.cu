@@ -212,6 +212,15 @@ int finish_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* hp, const floa
         ba.sparsity = u->sparsity; ba.sp_target = u->sparsity_target;
         ba.n_loss = (float)u->batch_global * r->V; ba.loss_out = loss_out;
     }
+    static const bool no_fuse = getenv("IMDBN_NO_FUSED_COLSTATS") != nullptr;
+    if (!no_fuse && tc_stats_packs(ctx, r, B) && (r->V % 4) == 0 && (r->H % 4) == 0 && al16(ea) && al16(eb)) {
+        // the statistics GEMM that follows packs its operands in one pass over these same matrices: the column
+        // statistics are computed there (k_pack_colstats); sq_part has colstat_blocks(r) >= tiles entries
+        static thread_local ColstatsJob job;
+        job.ea = ea; job.eb = eb; job.out = st_small; job.sq_part = sq_part; job.ticket = ctx->ticket; job.ba = ba;
+        ctx->colstats_job = &job;
+        return 0;
+    }
     IMDBN_CUDA(ctx, launch_pdl(k_colstats, dim3(nb), dim3(CS_COLS * CS_ROWS), 0, st, hp, hn, vp, vn, ea, eb, B,
                                r->V, r->H, st_small, sq_part, ctx->ticket, ba));
     IMDBN_CHECK_LAUNCH(ctx, "k_colstats");
@@ -638,12 +647,19 @@ int cd_core(imdbn_ctx* ctx, const imdbn_rbm* r, const float* data, int B, int k,
     // The bias / loss kernel and the weight-statistics kernel share only read-only inputs (the biases are
     // not read by the statistics GEMM, W is not read by the column statistics), so their order does not
     // matter; the column statistics go first and the tensor-core statistics kernel overlaps them.
+    ctx->act_hint = nullptr;
+    if (do_fwd && tail->next_data) {       // (exact mode) let the packing pass also scan the next minibatch
+        ctx->pack_scan = tail->next_data; ctx->pack_scan_rows = tail->B_next;
+    }
     rc = finish_stats(ctx, r, pos_h, h_prob, data, v_s, data, v_prob, B, st_small, sq_part, upd, loss_out,
                       stats_out == nullptr, st);                                        // :216-226
     if (rc) return rc;
     ctx->stats_after_colstats = true;
     rc = gemm_stats(ctx, r, data, pos_h, v_s, h_prob, B, stats_out, upd, st);           // :200,209,212
     ctx->stats_after_colstats = false;
+    ctx->pack_scan = nullptr; ctx->colstats_job = nullptr;
+    // ctx->act_hint (set by the packing pass when it scanned [data ; next_data]) applies to the forward pass below only
+    struct HintGuard { imdbn_ctx* c; ~HintGuard() { c->act_hint = nullptr; } } hint_guard{ctx};
     if (rc || !do_fwd) return rc;
     // one pass over the updated W for [data ; next_data]
     const float* src = data;

@@ -127,12 +127,6 @@ __global__ void k_groups(const float* __restrict__ logits, float* __restrict__ p
 // Block = 32 columns x 8 row lanes; every thread sums rows y, y+8, ...; the 8 lane sums are added in
 // lane order (deterministic).  One squared-error partial per block.
 constexpr int CS_COLS = 32, CS_ROWS = 8;
-struct BiasArgs {            // apply != 0: update the biases of the block's columns in the same kernel
-    int apply;
-    float* hb; float* hbm; float* vb; float* vbm;
-    float lr, mom, bsz; int sparsity; float sp_target;
-    float n_loss; float* loss_out;
-};
 __global__ void __launch_bounds__(CS_COLS * CS_ROWS)
 k_colstats(const float* __restrict__ hp, const float* __restrict__ hn, const float* __restrict__ vp,
            const float* __restrict__ vn, const float* __restrict__ ea, const float* __restrict__ eb, int B,

@@ -108,7 +108,8 @@ static const CUtensorMap* get_map(imdbn_ctx* ctx, const float* ptr, int inner, i
 // whole tile is exactly representable (binary states always are).  W_lo * a_lo (2^-22 relative) is dropped.
 constexpr int TS_BM = 128;                 // output features per tile (MMA M)
 constexpr int TS_MAX_STAGES = 8;
-constexpr int TS_NLO = 2;                  // W_lo buffers (exact mode)
+constexpr int TS_NLO = 4;                  // W_lo buffers (exact mode): a ring, so the converters never wait for products
+constexpr int TS_NGRP = 2;                 // converter groups of four warps, group g takes the iterations n % 2 == g
 constexpr int TS_BAR_BYTES = 512;
 template <bool SPLIT> struct TsCfg {
     static constexpr int BK = SPLIT ? 32 : 64;          // reduction elements per pipeline stage
@@ -126,6 +127,10 @@ struct StreamArgs {
     int nbuf;                              // TMEM accumulator sets (2 unless the batch tile is too wide)
     int stages;
     int blo;                               // exact mode: activation remainders are computed (0 = the caller knows them to be zero)
+    const uint32_t* hint; uint32_t hint_gen;   // nullable: hint[0], hint[1] != hint_gen  =>  the activations of THIS pass were
+                                           // found exactly representable by the operand-packing pass: take the blo = 0 layout
+    int stages_x;                          // ring depth of that layout
+    int bar_off;                           // byte offset of the barrier block (behind the larger of the two layouts)
     int dbg;                               // experiment switch (IMDBN_DEBUG_STREAM): 1 = converters idle, 2 = no lo products, 3 = both
     int l2_ahead;                          // iterations whose W boxes are prefetched into L2 ahead of the ring (0 = off)
     int w_stable;                          // W is not written by any kernel still in flight: prefetch it before the wait
@@ -156,18 +161,16 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     constexpr int TS_A_BYTES = TsCfg<SPLIT>::A_BYTES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int stage_bytes = ts_stage_bytes(a.Npad, SPLIT, a.blo != 0);
     const int b_bytes = a.Npad * TS_BK * 4;
-    uint8_t* lo_base = smem + a.stages * stage_bytes;                 // [TS_NLO][TS_A_BYTES] (exact mode)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(lo_base + (SPLIT ? TS_NLO * TS_A_BYTES : 0));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.bar_off);
     uint64_t* full = bars;                      // [TS_MAX_STAGES]
     uint64_t* empty = bars + 8;                 // [TS_MAX_STAGES]
     uint64_t* acc_full = bars + 16;             // [2]
     uint64_t* acc_empty = bars + 18;            // [2]
     uint64_t* lo_full = bars + 20;              // [TS_NLO]
-    uint64_t* lo_empty = bars + 22;             // [TS_NLO]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
-    volatile uint32_t* blo_flags = reinterpret_cast<volatile uint32_t*>(bars + 26);   // [TS_MAX_STAGES][4]
+    uint64_t* lo_empty = bars + 24;             // [TS_NLO]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+    volatile uint32_t* blo_flags = reinterpret_cast<volatile uint32_t*>(bars + 30);   // [TS_MAX_STAGES][4]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cta = blockIdx.x;
@@ -184,7 +187,7 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         if (a.B1) tma_prefetch_desc(&tmB2);
-        for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < TS_MAX_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
         for (int s = 0; s < TS_NLO; ++s) { mbar_init(&lo_full[s], 4); mbar_init(&lo_empty[s], 1); }
         fence_barrier_init();
@@ -195,6 +198,13 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (!a.w_stable) { pdl_wait(); pdl_trigger(); }    // everything above overlapped the previous kernel's tail
+    // layout of the ring: fixed by the host, or (exact mode, hint given) chosen here from the packing pass's verdict
+    int blo_on = a.blo, n_stages = a.stages;
+    if (SPLIT && a.hint != nullptr && __ldcg(a.hint) != a.hint_gen && __ldcg(a.hint + 1) != a.hint_gen) {
+        blo_on = 0; n_stages = a.stages_x;
+    }
+    const int stage_bytes = ts_stage_bytes(a.Npad, SPLIT, blo_on != 0);
+    uint8_t* lo_base = smem + n_stages * stage_bytes;                 // [TS_NLO][TS_A_BYTES] (exact mode)
 
     auto load_A = [&](int it, int stage) {
         const int tile = it / k_iters, kit = it - tile * k_iters;
@@ -239,24 +249,24 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint32_t tx = (uint32_t)(TS_A_BYTES + b_bytes);
             int pre = 0;
             // L2 prefetch is a hint on a coherent cache: safe even while an earlier kernel still writes W
-            const int pf0 = min(end - beg, a.stages + a.l2_ahead);
-            if (a.l2_ahead > 0) for (int i = a.w_stable ? a.stages : 0; i < pf0; ++i) prefetch_A(beg + i);
+            const int pf0 = min(end - beg, n_stages + a.l2_ahead);
+            if (a.l2_ahead > 0) for (int i = a.w_stable ? n_stages : 0; i < pf0; ++i) prefetch_A(beg + i);
             if (a.w_stable) {            // the weights of the first ring of stages stream in while the predecessor ends
-                pre = min(a.stages, end - beg);
+                pre = min(n_stages, end - beg);
                 for (int i = 0; i < pre; ++i) { mbar_expect_tx(&full[i], tx); load_A(beg + i, i); }
                 pdl_wait();
             }
             TS_MARK(1);
             int stage = 0; uint32_t phase = 0;
             for (int it = beg; it < end; ++it) {
-                if (a.l2_ahead > 0 && it + a.stages + a.l2_ahead < end) prefetch_A(it + a.stages + a.l2_ahead);
+                if (a.l2_ahead > 0 && it + n_stages + a.l2_ahead < end) prefetch_A(it + n_stages + a.l2_ahead);
                 if (it - beg >= pre) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_expect_tx(&full[stage], tx);
                     load_A(it, stage);
                 }
                 load_B(it, stage);
-                if (++stage == a.stages) { stage = 0; phase ^= 1; }
+                if (++stage == n_stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -283,7 +293,7 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const uint32_t sA = smem_u32(smem + p_stage * stage_bytes);
                 const uint32_t sB = sA + TS_A_BYTES, sBlo = sB + (uint32_t)b_bytes;
                 const uint32_t sAlo = smem_u32(lo_base + l * TS_A_BYTES);
-                const uint32_t blo = a.blo ? (blo_flags[p_stage * 4] | blo_flags[p_stage * 4 + 1] | blo_flags[p_stage * 4 + 2] |
+                const uint32_t blo = blo_on ? (blo_flags[p_stage * 4] | blo_flags[p_stage * 4 + 1] | blo_flags[p_stage * 4 + 2] |
                                               blo_flags[p_stage * 4 + 3]) : 0u;
                 // the remainder products (2^-11 of the main ones) have their own accumulator: added to the large
                 // running sum one by one they would each cost it a truncation
@@ -326,7 +336,7 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     } else {
                         mma_commit(&empty[stage]);                  // smem slot free when these MMAs retire
                     }
-                    if (++stage == a.stages) { stage = 0; phase ^= 1; }
+                    if (++stage == n_stages) { stage = 0; phase ^= 1; }
                 }
                 if (!SPLIT) mma_commit(&acc_full[buf]);
                 cur += n_it;
@@ -376,20 +386,21 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // barrier hand-over -- is several times the issue time).
         const int ct = (threadIdx.x - 192) & 127, cw = ct >> 5, grp = (threadIdx.x - 192) >> 7;
         const int nB4 = b_bytes / 16;
-        for (int it = beg + grp, n = grp; it < end; it += TS_NLO, n += TS_NLO) {
-            const int stage = n % a.stages;
-            const uint32_t phase = (uint32_t)(n / a.stages) & 1u;
+        for (int it = beg + grp, n = grp; it < end; it += TS_NGRP, n += TS_NGRP) {
+            const int l = n & (TS_NLO - 1);
+            const int stage = n % n_stages;
+            const uint32_t phase = (uint32_t)(n / n_stages) & 1u;
             const float4* sA = reinterpret_cast<const float4*>(smem + stage * stage_bytes);
             const float4* sB = reinterpret_cast<const float4*>(smem + stage * stage_bytes + TS_A_BYTES);
             float4* sBlo = reinterpret_cast<float4*>(smem + stage * stage_bytes + TS_A_BYTES + b_bytes);
-            float4* sAlo = reinterpret_cast<float4*>(lo_base + grp * TS_A_BYTES);
+            float4* sAlo = reinterpret_cast<float4*>(lo_base + l * TS_A_BYTES);
             mbar_wait(&full[stage], phase);
-            mbar_wait(&lo_empty[grp], ((n / TS_NLO) & 1) ^ 1);
+            mbar_wait(&lo_empty[l], ((n / TS_NLO) & 1) ^ 1);
             bool nz = false;
             if (!(a.dbg & 1)) {
 #pragma unroll
                 for (int i = 0; i < TS_A_BYTES / 16 / 128; ++i) sAlo[ct + i * 128] = tf32_lo4(sA[ct + i * 128]);
-                if (a.blo)
+                if (blo_on)
                 for (int i = ct; i < nB4; i += 128) {
                     const float4 lo = tf32_lo4(sB[i]);
                     nz |= (lo.x != 0.0f) | (lo.y != 0.0f) | (lo.z != 0.0f) | (lo.w != 0.0f);
@@ -400,7 +411,7 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (lane == 0) blo_flags[stage * 4 + cw] = nz ? 1u : 0u;
             if (!(a.dbg & 4)) fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's smem reads
             __syncwarp();
-            if (lane == 0) mbar_arrive(&lo_full[grp]);
+            if (lane == 0) mbar_arrive(&lo_full[l]);
         }
     }
 
@@ -480,7 +491,7 @@ int tc_plan_max_slabs(const SKPlan& p, int M_total) {
 template <bool A_MN, bool SPLIT>
 static int launch_stream(imdbn_ctx* ctx, const CUtensorMap* tmA, const CUtensorMap* tmB, const CUtensorMap* tmB2,
                          StreamArgs& a, int G, int chunks, cudaStream_t st) {
-    const size_t smem = ts_smem_bytes(a.Npad, a.stages, SPLIT, a.blo != 0);
+    const size_t smem = (size_t)a.bar_off + TS_BAR_BYTES + 1024;
     static size_t smem_set = 0;          // the attribute is sticky: raise it only when a larger size is needed
     if (smem > smem_set) {
         IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_tc_stream<A_MN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -514,6 +525,13 @@ static int stream_pass(imdbn_ctx* ctx, const imdbn_rbm* r, const float* act, int
     { static const int pf_env = getenv("IMDBN_L2_AHEAD") ? atoi(getenv("IMDBN_L2_AHEAD")) : 0; a.l2_ahead = pf_env * (64 / bk); }
     const int budget = 226 * 1024 - TS_BAR_BYTES - (split ? TS_NLO * TS_BM * 32 * 4 : 0);
     a.stages = std::max(2, std::min(split ? TS_MAX_STAGES : 4, budget / ts_stage_bytes(a.Npad, split, a.blo != 0)));
+    a.stages_x = a.stages;
+    if (a.blo && ctx->act_hint) {
+        a.hint = ctx->act_hint; a.hint_gen = ctx->act_hint_gen;
+        a.stages_x = std::max(2, std::min(TS_MAX_STAGES, budget / ts_stage_bytes(a.Npad, split, false)));
+    }
+    a.bar_off = std::max(a.stages * ts_stage_bytes(a.Npad, split, a.blo != 0), a.stages_x * ts_stage_bytes(a.Npad, split, false)) +
+                (split ? TS_NLO * TS_BM * 32 * 4 : 0);
     const int G = tc_plan_ctas(a.sk, M_total);
     // W is [V, H] row-major: inner = H.  up: boxes [bk k-rows x 32 h]; down: boxes [128 v-rows x 32 h]
     const CUtensorMap* tmA = get_map(ctx, r->W, r->H, r->V, up ? bk : TS_BM, up);
@@ -586,6 +604,9 @@ static PackSizes pack_sizes(const imdbn_rbm* r, int B, bool split) {
     p.total = p.pa + p.pa_lo + p.pb;
     return p;
 }
+bool tc_stats_packs(const imdbn_ctx* ctx, const imdbn_rbm* r, int B) {
+    return uses_tc(ctx) && tc_stats_supported(ctx, r, B) && !stats_wide(ctx, r, B);
+}
 size_t tc_ws_bytes(const imdbn_ctx* ctx, const imdbn_rbm* r, int B) {
     if (!uses_tc(ctx) || !tc_shape_ok(r, B) || stats_wide(ctx, r, B)) return 0;
     return pack_sizes(r, B, tc_split(ctx)).total + 512;
@@ -608,7 +629,7 @@ int tc_gemm_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* vp, const flo
     a.k_chunks = (B + ST_KC - 1) / ST_KC;
     if (upd) { a.lr = upd->lr; a.mom = upd->momentum; a.wd = upd->weight_decay; a.bsz = (float)upd->batch_global; }
     { static const int dbg_env = getenv("IMDBN_DEBUG_STATS") ? atoi(getenv("IMDBN_DEBUG_STATS")) : 0; a.dbg = dbg_env; }
-    const bool after_colstats = ctx->stats_after_colstats;
+    const bool after_colstats = ctx->stats_after_colstats || ctx->colstats_job != nullptr;
     a.late_wait = after_colstats ? 1 : 0;
     ctx->stats_after_colstats = false;
     a.w_policy = l2_policy_for(r);
@@ -641,9 +662,21 @@ int tc_gemm_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* vp, const flo
         const int n4 = (a.m_tiles + a.n_tiles) * 32;
         {
             ProfScope prof(ctx, IMDBN_KERNEL_PACK, r->V, r->H, st);
-            IMDBN_CUDA(ctx, launch_pdl(k_pack_ops, dim3((n4 + 255) / 256, a.k_chunks * ST_KC), dim3(256), 0, st, pk));
+            if (ctx->colstats_job) {       // the column statistics of this update ride along (one pass over the matrices)
+                pk.after_colstats = 1;
+                const bool scan = split && ctx->pack_scan != nullptr && aligned16(ctx->pack_scan);
+                if (scan) { pk.scan = ctx->pack_scan; pk.scan_rows = ctx->pack_scan_rows; }
+                ctx->act_hint = scan ? ctx->pack_flags : nullptr;
+                ctx->act_hint_gen = pk.gen;
+                IMDBN_CUDA(ctx, launch_pdl(k_pack_colstats, dim3(a.m_tiles + a.n_tiles + (scan ? a.m_tiles : 0)),
+                                           dim3(32 * PC_ROWS), 0, st, pk, *ctx->colstats_job));
+            } else {
+                IMDBN_CUDA(ctx, launch_pdl(k_pack_ops, dim3((n4 + 255) / 256, a.k_chunks * ST_KC), dim3(256), 0, st, pk));
+            }
         }
-        IMDBN_CHECK_LAUNCH(ctx, "k_pack_ops");
+        ctx->colstats_job = nullptr;
+        ctx->pack_scan = nullptr;
+        IMDBN_CHECK_LAUNCH(ctx, "k_pack");
         a.pa = pk.pa; a.pa_lo = pk.pa_lo; a.pb = pk.pb; a.flags = pk.flags; a.gen = pk.gen;
     }
     const int G = std::min(tc_sms(ctx), a.m_tiles * a.n_tiles);

@@ -9,6 +9,8 @@ bool tc_up_supported(const imdbn_ctx* ctx, const imdbn_rbm* r, int B);
 bool tc_down_supported(const imdbn_ctx* ctx, const imdbn_rbm* r, int B);
 bool tc_stats_supported(const imdbn_ctx* ctx, const imdbn_rbm* r, int B);
 size_t tc_ws_bytes(const imdbn_ctx* ctx, const imdbn_rbm* r, int B);
+// the statistics call for this shape packs its operands (and can take the column statistics along: ColstatsJob)
+bool tc_stats_packs(const imdbn_ctx* ctx, const imdbn_rbm* r, int B);
 
 // v2 != nullptr: the batch is [v (B1 rows) ; v2 (B - B1 rows)] read from two matrices (B1 % 8 == 0, B <= 256)
 int tc_gemm_up(imdbn_ctx* ctx, const imdbn_rbm* r, const float* v, int B, float* part, cudaStream_t st,

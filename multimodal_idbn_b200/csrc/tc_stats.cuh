@@ -68,6 +68,7 @@ struct PackArgs {
     int B, V, H, m_tiles, n_tiles, k_chunks, split;
     uint8_t* pa; uint8_t* pa_lo; uint8_t* pb;
     uint32_t* flags; uint32_t gen;
+    const float* scan; int scan_rows;      // nullable [scan_rows, V]: only scanned; flags[1] = gen if some value is inexact
     int after_colstats;      // the predecessor triggered only after its own wait: dependents may be released at once
 };
 
@@ -114,6 +115,158 @@ __global__ void __launch_bounds__(256) k_pack_ops(PackArgs a) {
         if (a.split) {
             *reinterpret_cast<float4*>(a.pb + piece + 2 * SEG_B + box_off) = tf32_lo4(x0);
             *reinterpret_cast<float4*>(a.pb + piece + 3 * SEG_B + box_off) = tf32_lo4(x1);
+        }
+    }
+}
+
+// k_pack_ops fused with the column statistics of the CD update (k_colstats, rbm.py:216-226 / 478-483): the two passes
+// read the same four matrices.  One block = one 128-column block of the v side or of the h side, all batch rows;
+// thread = (float4 column, row lane): rows lane, lane + 8, ... are packed and summed by one thread, the eight lanes
+// are added in lane order (the summation order of k_colstats, so dh / dv / sum pos_h are bit-identical to it); the
+// biases of the block's columns are updated in place, the squared error goes through per-block partials and a ticket.
+constexpr int PC_ROWS = 8;
+__global__ void __launch_bounds__(32 * PC_ROWS) k_pack_colstats(PackArgs a, ColstatsJob cs) {
+    __shared__ float4 red[2][PC_ROWS][32];
+    __shared__ float red_sq[PC_ROWS][32];
+    __shared__ unsigned int s_last;
+    // trigger AFTER the wait (see k_colstats): the statistics kernel launched next may start at once -- its weight
+    // stream shares nothing with this kernel, its operand path waits for this kernel's completion
+    pdl_wait();
+    pdl_trigger();
+    const int lane = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    if ((int)blockIdx.x >= a.m_tiles + a.n_tiles) {
+        // scan blocks: is the NEXT minibatch exactly representable in tf32?  (it joins `vp` in the forward pass that
+        // follows the update; that pass then needs no remainder tiles for its activations)
+        const int c = (blockIdx.x - a.m_tiles - a.n_tiles) * 128 + 4 * lane;
+        bool bad = false;
+        if (c < a.V)
+            for (int r = ry; r < a.scan_rows; r += PC_ROWS) {
+                const float4 l = tf32_lo4(*reinterpret_cast<const float4*>(a.scan + (size_t)r * a.V + c));
+                bad |= (l.x != 0.f) | (l.y != 0.f) | (l.z != 0.f) | (l.w != 0.f);
+            }
+        if (bad) a.flags[1] = a.gen;
+        return;
+    }
+    const bool is_a = (int)blockIdx.x < a.m_tiles;
+    const int tile = is_a ? blockIdx.x : blockIdx.x - a.m_tiles;
+    const int W = is_a ? a.V : a.H;
+    const int col = tile * 128 + 4 * lane;
+    const int cb = lane >> 3, j = lane & 7;
+    const float* s0 = is_a ? a.vp : a.hp;
+    const float* s1 = is_a ? a.vn : a.hn;
+    const bool load_ea = is_a && cs.ea != a.vp, load_eb = is_a && cs.eb != a.vn;
+    constexpr int SEG_B = st_seg_b<128>();
+    const size_t piece_bytes = is_a ? (size_t)(2 * ST_SEG_A) : (size_t)((a.split ? 4 : 2) * SEG_B);
+    const uint32_t seg = is_a ? ST_SEG_A : SEG_B;
+    uint8_t* dst = is_a ? a.pa : a.pb;
+    float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
+    float sq = 0.f;
+    bool nz = false;
+    const int rows = a.k_chunks * ST_KC;
+    constexpr int UN = 4;                          // rows in flight per thread: all their loads are issued together
+    for (int r0 = ry; r0 < rows; r0 += PC_ROWS * UN) {
+        float4 x0[UN], x1[UN], e1[UN];
+        bool valid[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int r = r0 + u * PC_ROWS;
+            valid[u] = r < a.B && col < W;
+            x0[u] = x1[u] = e1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid[u]) {
+                const size_t o = (size_t)r * W + col;
+                x0[u] = *reinterpret_cast<const float4*>(s0 + o);
+                x1[u] = *reinterpret_cast<const float4*>(s1 + o);
+                if (load_eb) e1[u] = *reinterpret_cast<const float4*>(cs.eb + o);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int r = r0 + u * PC_ROWS;
+            if (r >= rows) break;
+            const int kc = r / ST_KC, k = r % ST_KC;
+            if (valid[u]) {
+                t0.x += x0[u].x; t0.y += x0[u].y; t0.z += x0[u].z; t0.w += x0[u].w;
+                t1.x += x1[u].x; t1.y += x1[u].y; t1.z += x1[u].z; t1.w += x1[u].w;
+                if (is_a) {
+                    const float4 e0 = load_ea ? *reinterpret_cast<const float4*>(cs.ea + (size_t)r * W + col) : x0[u];
+                    const float4 ee = load_eb ? e1[u] : x1[u];
+                    float d;
+                    d = e0.x - ee.x; sq = fmaf(d, d, sq); d = e0.y - ee.y; sq = fmaf(d, d, sq);
+                    d = e0.z - ee.z; sq = fmaf(d, d, sq); d = e0.w - ee.w; sq = fmaf(d, d, sq);
+                }
+            }
+            const uint32_t box_off = (uint32_t)cb * ST_OP_BOX + (uint32_t)k * 128u +
+                                     ((((uint32_t)j >> 1) ^ (uint32_t)(k & 3)) << 5) + (((uint32_t)j & 1u) << 4);
+            const size_t piece = ((size_t)tile * a.k_chunks + kc) * piece_bytes;
+            *reinterpret_cast<float4*>(dst + piece + box_off) = x0[u];
+            *reinterpret_cast<float4*>(dst + piece + seg + box_off) = x1[u];
+            if (a.split) {
+                const float4 l0 = tf32_lo4(x0[u]), l1 = tf32_lo4(x1[u]);
+                if (is_a) {
+                    *reinterpret_cast<float4*>(a.pa_lo + piece + box_off) = l0;
+                    *reinterpret_cast<float4*>(a.pa_lo + piece + seg + box_off) = l1;
+                    nz |= (l0.x != 0.f) | (l0.y != 0.f) | (l0.z != 0.f) | (l0.w != 0.f) |
+                          (l1.x != 0.f) | (l1.y != 0.f) | (l1.z != 0.f) | (l1.w != 0.f);
+                } else {
+                    *reinterpret_cast<float4*>(dst + piece + 2 * seg + box_off) = l0;
+                    *reinterpret_cast<float4*>(dst + piece + 3 * seg + box_off) = l1;
+                }
+            }
+        }
+    }
+    if (nz) a.flags[0] = a.gen;
+    red[0][ry][lane] = t0; red[1][ry][lane] = t1; red_sq[ry][lane] = sq;
+    __syncthreads();
+    if (ry == 0) {
+        float p[4] = {0.f, 0.f, 0.f, 0.f}, n[4] = {0.f, 0.f, 0.f, 0.f};
+        float s = 0.f;
+#pragma unroll
+        for (int q = 0; q < PC_ROWS; ++q) {
+            const float4 u = red[0][q][lane], v = red[1][q][lane];
+            p[0] += u.x; p[1] += u.y; p[2] += u.z; p[3] += u.w;
+            n[0] += v.x; n[1] += v.y; n[2] += v.z; n[3] += v.w;
+            s += red_sq[q][lane];
+        }
+        const BiasArgs& ba = cs.ba;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int c = col + e;
+            if (c >= W) break;
+            const float d = p[e] - n[e];
+            if (is_a) {
+                cs.out[a.H + c] = d;
+                if (ba.apply) {                               // rbm.py:223-224 / 480-481
+                    const float m = add_rn(mul_rn(ba.vbm[c], ba.mom), mul_rn(ba.lr, d) / ba.bsz);
+                    ba.vbm[c] = m;
+                    ba.vb[c] = add_rn(ba.vb[c], m);
+                }
+            } else {
+                cs.out[c] = d; cs.out[a.H + a.V + c] = p[e];
+                if (ba.apply) {                               // rbm.py:216-220 / 478-479
+                    float m = add_rn(mul_rn(ba.hbm[c], ba.mom), mul_rn(ba.lr, d) / ba.bsz);
+                    if (ba.sparsity) m = add_rn(m, mul_rn(-ba.lr, add_rn(p[e] / ba.bsz, -ba.sp_target)));
+                    ba.hbm[c] = m;
+                    ba.hb[c] = add_rn(ba.hb[c], m);
+                }
+            }
+        }
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) {
+            cs.sq_part[blockIdx.x] = s;                       // (h-side blocks contribute 0)
+            __threadfence();
+            s_last = (atomicAdd(cs.ticket, 1u) == (unsigned)(a.m_tiles + a.n_tiles) - 1) ? 1u : 0u;
+        }
+        __syncwarp();
+        if (s_last) {                                         // last block: partials in index order (deterministic)
+            __threadfence();
+            float v = 0.f;
+            for (int i = lane; i < a.m_tiles; i += 32) v += __ldcg(cs.sq_part + i);
+            for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) {
+                cs.out[2 * a.H + a.V] = v;
+                if (ba.loss_out) *ba.loss_out = v / ba.n_loss;
+                *cs.ticket = 0u;
+            }
         }
     }
 }
