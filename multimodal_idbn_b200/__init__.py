@@ -13,6 +13,7 @@ from .idbn import iDBN, prefetch_to_device
 from .imdbn import iMDBN
 from .imdbn_bimodal import iMDBN_BiModal
 from . import dist
+from . import datasets
 
 # Checkpoints must cross-load with the reference: classes pickle under the reference's
 # module paths, which the ``imdbn`` alias package at the repository root resolves to these classes.
@@ -21,5 +22,5 @@ iDBN.__module__ = "imdbn.models.idbn"
 iMDBN.__module__ = "imdbn.models.imdbn"
 iMDBN_BiModal.__module__ = "imdbn.models.imdbn_bimodal"
 
-__all__ = ["RBM", "iDBN", "iMDBN", "iMDBN_BiModal", "rbm_free_energy", "random_field", "prefetch_to_device", "dist",
+__all__ = ["RBM", "iDBN", "iMDBN", "iMDBN_BiModal", "rbm_free_energy", "random_field", "prefetch_to_device", "dist", "datasets",
            "set_precision", "get_precision", "load_library", "total_launches", "LIB_PATH"]

@@ -46,7 +46,7 @@ PassPlan plan_pass(const imdbn_ctx* ctx, const imdbn_rbm* r, int B, bool up) {
     const bool tc = uses_tc(ctx) &&
                     (up ? tc_up_supported(ctx, r, B) : tc_down_supported(ctx, r, B));
     if (tc) {
-        p.sk = tc_plan(ctx, N, K);
+        p.sk = tc_plan(ctx, N, K, B);
         p.splits = tc_plan_max_slabs(p.sk, N);
         p.kps = 0;
     } else {

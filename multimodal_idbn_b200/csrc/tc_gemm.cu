@@ -462,14 +462,18 @@ bool tc_stats_supported(const imdbn_ctx* ctx, const imdbn_rbm* r, int B) {
     return tc_shape_ok(r, B) && tc_state(const_cast<imdbn_ctx*>(ctx))->encode != nullptr;
 }
 
-SKPlan tc_plan(const imdbn_ctx* ctx, int M_total, int K_total) {
+SKPlan tc_plan(const imdbn_ctx* ctx, int M_total, int K_total, int B) {
     SKPlan p;
     const int bk = ts_bk(tc_split(ctx));
     const int m_tiles = (M_total + TS_BM - 1) / TS_BM;
     p.k_iters = (K_total + bk - 1) / bk;
     const int total = m_tiles * p.k_iters;
     // at least 256 reduction elements per CTA: fewer, longer ranges for small layers (fewer slabs to add)
-    const int G = std::max(1, std::min(tc_sms(ctx), total / (256 / bk)));
+    int G = std::max(1, std::min(tc_sms(ctx), total / (256 / bk)));
+    // Large batches are cut into 256-row chunks on blockIdx.y: once (chunks x output tiles) fills the chip, splitting
+    // K as well only multiplies the partial slabs (12 slabs of 134 MB each per pass at batch 8192 on 10000 -> 4096)
+    const int chunks = (B + 255) / 256;
+    if (B > 256 && chunks * m_tiles >= tc_sms(ctx)) G = m_tiles;
     p.q = total / G;
     p.r = total % G;
     p.tile_w = TS_BM;
@@ -513,7 +517,7 @@ static int stream_pass(imdbn_ctx* ctx, const imdbn_rbm* r, const float* act, int
     StreamArgs a{};
     a.M_total = M_total; a.K_total = K_total; a.B = B; a.Npad = B > 256 ? 256 : npad_of(B);
     const int chunks = (B + a.Npad - 1) / a.Npad;
-    a.sk = tc_plan(ctx, M_total, K_total);
+    a.sk = tc_plan(ctx, M_total, K_total, B);
     a.total_iters = ((M_total + TS_BM - 1) / TS_BM) * a.sk.k_iters;
     a.part = part;
     a.nbuf = (split ? 4 : 2) * a.Npad <= 512 ? 2 : 1;

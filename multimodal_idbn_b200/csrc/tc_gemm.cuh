@@ -21,7 +21,7 @@ int tc_gemm_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* vp, const flo
                   cudaStream_t st);
 void tc_destroy(imdbn_ctx* ctx);
 // stream-K plan of a tensor-core pass producing M_total output features from K_total inputs
-SKPlan tc_plan(const imdbn_ctx* ctx, int M_total, int K_total);
+SKPlan tc_plan(const imdbn_ctx* ctx, int M_total, int K_total, int B);
 int tc_plan_max_slabs(const SKPlan& p, int M_total);
 
 // two streams on disjoint SM sets (CUDA green contexts); see imdbn_sm_partition in the public header

@@ -50,7 +50,8 @@ def prefetch_to_device(loader: Iterable, device, ring: int = 4):
     (A worker-thread variant was measured and dropped: 183 us per C2 step against 140-150 us -- the GIL hand-offs
     cost more than the ~20 us of staging work they take off the consumer thread.)"""
     device = torch.device(device)
-    if device.type != "cuda":
+    if device.type != "cuda" or getattr(loader, "device_resident", False):
+        # (datasets.DeviceLoader: the batches are views of a matrix that already lives in HBM)
         for batch in loader:
             yield batch
         return

@@ -197,3 +197,34 @@ def test_reference_acceptance_script_checks(M, tmp_path, monkeypatch):
     assert idbn.represent(x).shape == (8, 100)
     assert idbn.reconstruct(x).shape == (8, 784)
     assert idbn.decode(torch.randn(8, 100).to(dev)).shape == (8, 784)
+
+
+def test_device_resident_loader_trains_like_a_host_loader(M, tmp_path, monkeypatch):
+    """iDBN.train fed by datasets.DeviceLoader (batches = views of a matrix in HBM, no host->device copy) gives the
+    same parameters, bit for bit, as the same data through a torch DataLoader; iMDBN.train_joint accepts it too."""
+    monkeypatch.chdir(tmp_path)
+    from multimodal_idbn_b200.datasets import DeviceDataset, DeviceLoader
+    g = torch.Generator().manual_seed(5)
+    x = (torch.rand(44, 1, 8, 8, generator=g) < 0.2).float()
+    y = torch.nn.functional.one_hot(torch.randint(0, 4, (44,), generator=g), 4).float()
+    runs = []
+    for kind in ("host", "device"):
+        torch.manual_seed(0)
+        if kind == "host":
+            dl = _loader(x, y, 8)
+        else:
+            dl = DeviceLoader(DeviceDataset(x, y, DEV), 8, shuffle=False)
+        m = M.iDBN([64, 32, 16], dict(PARAMS), dl, None, torch.device(DEV))
+        for i, l in enumerate(m.layers):
+            l.set_rng(11 + i, 0)
+        m.train(2)
+        torch.cuda.synchronize()
+        runs.append([l.W.detach().cpu().clone() for l in m.layers] + [l.hid_bias.detach().cpu().clone() for l in m.layers])
+    for a, b in zip(*runs):
+        assert torch.equal(a, b)
+    dl = DeviceLoader(DeviceDataset(x, y, DEV), 8, shuffle=True, seed=1)
+    jm = M.iMDBN([64, 32, 16], 12, params=dict(PARAMS), dataloader=dl, val_loader=None, device=torch.device(DEV),
+                 num_labels=4)
+    jm.train_joint(2)
+    torch.cuda.synchronize()
+    assert torch.isfinite(jm.joint_rbm.W).all()

@@ -191,3 +191,44 @@ def test_reference_pickle_resolves_to_drop_in_classes():
     assert not hasattr(r, "_rng_seed")                 # a reference object: no drop-in extras yet
     r._next_rng()                                      # ...which the drop-in creates on first use
     assert r._rng_stream == 1
+
+
+def test_device_resident_dataset_and_loaders(tmp_path):
+    """datasets.py host logic, on the CPU device: npz loading, one-hot labels from numerosities,
+    seeded split, Subset-like validation set with the feature lists iDBN.__init__ reads (idbn.py:131-137), one
+    permutation per epoch, contiguous batch views with a ragged last batch, and the reference scripts' import path."""
+    import numpy as np
+    import torch
+    from imdbn.datasets.uniform_dataset import create_dataloaders_uniform
+    from multimodal_idbn_b200.datasets import DeviceLoader, DeviceDataset
+    rng = np.random.default_rng(0)
+    N, K = 53, 8
+    imgs = (rng.random((N, 10, 10)) < 0.1).astype(np.uint8)
+    nums = rng.integers(1, K + 1, size=N)
+    np.savez(tmp_path / "toy.npz", D=imgs, N_list=nums, cumArea_list=rng.random(N), CH_list=rng.random(N),
+             density_list=rng.random(N))
+    tr, va, te = create_dataloaders_uniform(str(tmp_path), "toy.npz", batch_size=8, num_workers=3, multimodal_flag=True,
+                                            device="cpu", seed=3)
+    assert len(tr.dataset) + len(va.dataset) + len(te.dataset) == N
+    assert sorted(tr.dataset.indices + va.dataset.indices + te.dataset.indices) == list(range(N))
+    base = va.dataset.dataset
+    assert len(base.labels) == N and len(base.cumArea_list) == N and len(base.CH_list) == N and len(base.density_list) == N
+    assert [base.labels[i] for i in va.dataset.indices] == [int(nums[i]) for i in va.dataset.indices]
+    # epoch = one permutation; every sample exactly once; last batch ragged; labels follow their images
+    seen, batches = [], list(tr)
+    assert len(batches) == len(tr) and batches[-1][0].shape[0] == len(tr.dataset) - 8 * (len(tr) - 1)
+    for xb, yb in batches:
+        assert xb.shape[1:] == (10, 10) and yb.shape[1] == K and xb.dtype == torch.float32 and xb.is_contiguous()
+        for x, y in zip(xb, yb):
+            hits = [i for i in tr.dataset.indices if np.array_equal(imgs[i], x.numpy().astype(np.uint8))
+                    and int(nums[i]) - 1 == int(y.argmax())]
+            assert hits
+            seen.append(hits[0])
+    first = torch.cat([b[0] for b in batches])
+    second = torch.cat([b[0] for b in tr])
+    assert first.shape == second.shape and not torch.equal(first, second)          # reshuffled next epoch
+    assert torch.equal(torch.cat([b[0] for b in va]), torch.cat([b[0] for b in va]))  # validation order is fixed
+    # a plain loader over a whole dataset, flat views
+    ds = DeviceDataset(torch.from_numpy(imgs), torch.from_numpy(nums), "cpu")
+    xb, yb = next(iter(DeviceLoader(ds, 5, flat=True)))
+    assert xb.shape == (5, 100) and torch.equal(xb, ds.images[:5]) and xb.data_ptr() == ds.images.data_ptr()
