@@ -649,7 +649,24 @@ def dp_block(M, dev, rank, world, precision, barrier, max_over_ranks):
                                  "ms_per_step": ms, "samples_per_s": Bgl / (ms * 1e-3),
                                  "tflops_total": fl / (ms * 1e-3) / 1e12,
                                  "note": "compare with extra.c5_large_batch.layers['L0 10000->4096']['8192'] of the 1-GPU run"}
-    del rl, xl
+    del xl
+    torch.cuda.empty_cache()
+    # ---- (4) the same layer, weak scaling: 8192 rows per GPU (global batch 8192 x N)
+    xw = (torch.rand(Bgl, Vl, device=dev) < 0.1).float()
+    for _ in range(2):
+        rl.train_epoch(xw, 0, 1, CD=k)
+    barrier()
+    n = 2
+    e0.record()
+    for _ in range(n):
+        rl.train_epoch(xw, 0, 1, CD=k)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / n
+    out["large_batch_weak"] = {"workload": f"RBM {Vl}->{Hl} CD-{k}, {Bgl} rows per GPU (global batch {Bgl * world}), tf32",
+                               "ms_per_step": ms, "samples_per_s": Bgl * world / (ms * 1e-3),
+                               "tflops_total": fl * world / (ms * 1e-3) / 1e12}
+    del rl, xw
     torch.cuda.empty_cache()
     M.dist.disable()
     M.set_precision(precision)

@@ -228,3 +228,32 @@ def test_device_resident_loader_trains_like_a_host_loader(M, tmp_path, monkeypat
     jm.train_joint(2)
     torch.cuda.synchronize()
     assert torch.isfinite(jm.joint_rbm.W).all()
+
+
+def test_label_clamped_trajectory_vs_oracle(M, tmp_path, monkeypatch):
+    """imdbn_logging's inline label-clamped Bernoulli chains (imdbn_logging.py:303-311, 465-476, 767-775), batched on
+    the chain kernel, against the oracle's conditional step (itself pinned by the cond_gibbs fixture)."""
+    monkeypatch.chdir(tmp_path)
+    from multimodal_idbn_b200.imdbn_logging import label_clamped_trajectory
+    from oracle import rbm_oracle as O
+    from oracle.philox import RandomField
+    g = load_golden("panel")
+    x, y = T(g["x"]), T(g["y"])
+    m = _small_imdbn(M, g, "l", x, y)
+    load_params(m.joint_rbm, g, "joint_")
+    m.z_class_mean = T(g["z_class_mean"]).to(DEV)
+    jr = m.joint_rbm
+    yb = y[:6]
+    jr.set_rng(77, 5)
+    z_traj, imgs = label_clamped_trajectory(m, yb, steps=7, decode=True)
+    assert z_traj.shape == (8, 6, 10) and imgs.shape == (8, 6, 40)
+    st = O.RBMState(T(g["joint_W"]), T(g["joint_hb"]), T(g["joint_vb"]), None, None, None, groups=[(10, 14)])
+    vk = torch.zeros(6, 14); km = torch.zeros(6, 14); vk[:, 10:] = yb; km[:, 10:] = 1
+    v = vk.clone(); v[:, :10] = T(g["z_class_mean"])[yb.argmax(1)]
+    ref = [v[:, :10].clone()]
+    for t in range(7):
+        v, _ = O.gibbs_conditional_step(st, v, vk, km, sample_h=True, sample_v=False, fld=RandomField(77, 5 + t))
+        ref.append(v[:, :10].clone())
+    close(z_traj, torch.stack(ref, 0), dict(rtol=1e-4, atol=1e-5))
+    layers = [O.RBMState(T(g[f"l{i}_W"]), T(g[f"l{i}_hb"]), T(g[f"l{i}_vb"]), None, None, None) for i in range(2)]
+    close(imgs[-1], O.idbn_decode(layers, ref[-1]), dict(rtol=1e-4, atol=1e-5))
