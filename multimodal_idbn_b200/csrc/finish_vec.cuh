@@ -18,16 +18,18 @@ __device__ __forceinline__ float sigmoid_t(float x) {
 template <bool FAST>
 __device__ __forceinline__ float div_t(float x, float T, float invT) { return FAST ? x * invT : div_by(x, T, invT); }
 
+// The loads of up to 16 slabs are issued together (one L2 round trip instead of one per group of four -- the finish
+// sits on the critical path between two passes); the additions stay in slab order.
 __device__ __forceinline__ float4 sum_slabs4(const float* __restrict__ part, int ns, size_t stride, size_t i) {
     float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s0 = 0; s0 < ns; s0 += 4) {
-        float4 v[4];
+    for (int s0 = 0; s0 < ns; s0 += 16) {
+        float4 v[16];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-            v[u] = (s0 + u < ns) ? *reinterpret_cast<const float4*>(part + (size_t)(s0 + u) * stride + i)
+        for (int u = 0; u < 16; ++u)
+            v[u] = (s0 + u < ns) ? __ldcg(reinterpret_cast<const float4*>(part + (size_t)(s0 + u) * stride + i))
                                  : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < 16; ++u)
             if (s0 + u < ns) { x.x += v[u].x; x.y += v[u].y; x.z += v[u].z; x.w += v[u].w; }
     }
     return x;

@@ -473,7 +473,9 @@ SKPlan tc_plan(const imdbn_ctx* ctx, int M_total, int K_total, int B) {
     // Large batches are cut into 256-row chunks on blockIdx.y: once (chunks x output tiles) fills the chip, splitting
     // K as well only multiplies the partial slabs (12 slabs of 134 MB each per pass at batch 8192 on 10000 -> 4096)
     const int chunks = (B + 255) / 256;
-    if (B > 256 && 4 * chunks * m_tiles >= 3 * tc_sms(ctx)) G = m_tiles;
+    // (not in the exact mode: the tensor core's accumulator truncates, so the shorter accumulation chains of the
+    // split are part of its error budget)
+    if (!tc_split(ctx) && B > 256 && 4 * chunks * m_tiles >= 3 * tc_sms(ctx)) G = m_tiles;
     p.q = total / G;
     p.r = total % G;
     p.tile_w = TS_BM;
