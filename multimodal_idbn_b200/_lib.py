@@ -261,8 +261,26 @@ def context_for_stream(device_index: int, stream_handle: int) -> "Context":
     return ctx
 
 
+_private_contexts = []
+
+
+def private_context(device_index: int) -> "Context":
+    """A context of its own (workspace, SM limit) that no other caller on the same stream shares; counted by
+    ``total_launches``."""
+    import weakref
+    ctx = Context(device_index)
+    ctx.set_precision(_precision)
+    _private_contexts.append(weakref.ref(ctx))
+    return ctx
+
+
 def total_launches() -> int:
-    return sum(c.launch_count() for c in _contexts.values())
+    n = sum(c.launch_count() for c in _contexts.values())
+    for ref in _private_contexts:
+        c = ref()
+        if c is not None:
+            n += c.launch_count()
+    return n
 
 
 def ptr(t: Optional[torch.Tensor]):

@@ -276,16 +276,16 @@ class iDBN:
                 st["ctx1"].set_sm_limit(n_small)
                 st["streams"] = [torch.cuda.ExternalStream(big, device=dev), torch.cuda.ExternalStream(small, device=dev)]
             elif piped:
+                # PRIVATE contexts (not the shared per-stream ones): an SM limit set on a shared context would leak
+                # into every other call on that stream
                 side = torch.cuda.Stream(device=dev)
-                with torch.cuda.stream(side):
-                    st["ctx1"], st["s1"] = L.context_for(v)
+                st["ctx0"] = L.private_context(idx)
+                st["ctx1"], st["s1"] = L.private_context(idx), side.cuda_stream
                 st["streams"] = [side]
                 st["early"] = 0
-                ctx_c.set_sm_limit(max(8, n_sms - reserve) if reserve > 0 else 0)
+                st["ctx0"].set_sm_limit(max(8, n_sms - reserve) if reserve > 0 else 0)
                 if reserve > 0:              # the side stream's persistent grids stay inside the SMs left to them
                     st["ctx1"].set_sm_limit(reserve)
-            else:
-                ctx_c.set_sm_limit(0)
             self._fused = st
             self._side_stream = st["streams"]
         par = st["parity"]

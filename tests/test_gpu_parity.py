@@ -606,4 +606,4 @@ def test_pipelining_without_sm_partition_fallback():
                           "train_step_variants"], env=env, capture_output=True, text=True, timeout=600,
                          cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-1000:]
-    assert "2 passed" in out.stdout
+    assert "6 passed" in out.stdout            # 3 precisions x the 2 modes of the fixture
