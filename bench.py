@@ -453,12 +453,20 @@ def c4_metric(M, dev, n_chains, world, steps=50, K=64):
                                  "engine": "k_label_gibbs: fp32 FFMA on the 32 x 256 label block (the clamped z enters "
                                            "once through one up-pass GEMM); tensor_frac is against the TF32 peak for scale"}
     r._mu_pull = {"mu_k": mu, "eta0": 0.15}
-    ms = _timed(lambda: r.noisy_meanfield_annealed(vk2, km2, n_steps=steps, clamp_suffix=Dz), 3)
-    cps = n_chains * steps / (ms * 1e-3)
-    out["txt2img_noisy_mf"] = {"chain_steps_per_s": cps * world, "ms": ms, "min_tflops": cps * 4 * Dz * H / 1e12,
-                               "tensor_frac": cps * 4 * Dz * H / 1e12 / peak,
-                               "sfu_ops_per_chain_step": 2 * (H + Dz) + Dz + H,
-                               "note": "per chain-step 2 (H + Dz) Box-Muller special-function ops + H + Dz sigmoids"}
+    prev = M.get_precision()
+    out["txt2img_noisy_mf"] = {}
+    for mode in dict.fromkeys(("tf32", prev)):
+        M.set_precision(mode)
+        ms = _timed(lambda: r.noisy_meanfield_annealed(vk2, km2, n_steps=steps, clamp_suffix=Dz), 3)
+        cps = n_chains * steps / (ms * 1e-3)
+        out["txt2img_noisy_mf"][mode] = {
+            "chain_steps_per_s": cps * world, "ms": ms, "min_tflops": cps * 4 * Dz * H / 1e12,
+            "tensor_frac": cps * 4 * Dz * H / 1e12 / peak,
+            "engine": ("k_chain_tc: ONE persistent tcgen05 kernel, 48 chains per CTA, state in shared memory as the MMA operand"
+                       if mode == "tf32" else "stepped: two k_tc_stream GEMMs + finish kernels per step (exact mode)")}
+    M.set_precision(prev)
+    out["txt2img_noisy_mf"]["bound"] = ("instruction issue, not the tensor pipe: per chain-step (H + Dz) = 756 Gaussian draws "
+                                       "(Philox4x32-10 + Box-Muller) and sigmoids, ~1e5 thread instructions")
     r._mu_pull = None
     # best-of-K through the product API
     items = max(1, n_chains // K)

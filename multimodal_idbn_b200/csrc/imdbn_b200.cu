@@ -426,6 +426,20 @@ int run_chain(imdbn_ctx* ctx, const imdbn_rbm* r, const imdbn_chain* ch, int B, 
     IMDBN_ARG(ctx, ch->n_steps >= 0 && ch->n_steps <= CHAIN_MAX_STEPS);
     IMDBN_ARG(ctx, ch->v_known && ch->known_mask);
     if (chain_is_label_only(r, ch, vprob_out)) return run_chain_label_only(ctx, r, ch, B, v_out, vprob_out, key, st);
+    if (!vprob_out && tc_chain_supported(ctx, r, ch, B)) {
+        // TXT->IMG annealing of many chains: one persistent tensor-core kernel, state in shared memory (chain_tc.cuh)
+        IMDBN_ARG(ctx, ch->T && ch->sigma);
+        const int n = ch->n_steps;
+        std::vector<float> host(3 * (size_t)n, 0.0f);
+        for (int t = 0; t < n; ++t) {
+            host[t] = fmaxf(1e-6f, ch->T[t]);
+            host[n + t] = ch->sigma[t];
+            host[2 * n + t] = ch->eta ? ch->eta[t] : 0.0f;
+        }
+        IMDBN_CUDA(ctx, cudaMemcpyAsync(tables, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+        ProfScope prof(ctx, IMDBN_KERNEL_CHAIN, r->V, r->H, st);
+        return tc_chain_t2i(ctx, r, ch, B, v_out, key, tables, tables + n, tables + 2 * n, st);
+    }
     if (chain_is_stepped(ctx, r, ch, B)) return run_chain_stepped(ctx, r, ch, B, v_out, vprob_out, key, st);
     ChainArgs a{};
     a.W = r->W; a.Wt = Wt; a.hb = r->hb; a.vb = r->vb;

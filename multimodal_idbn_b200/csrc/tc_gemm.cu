@@ -711,6 +711,48 @@ int tc_gemm_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* vp, const flo
     return 0;
 }
 
+#include "chain_tc.cuh"
+
+// TXT->IMG noisy mean-field chains as one persistent kernel (chain_tc.cuh): single-pass tf32, label block clamped
+bool tc_chain_supported(const imdbn_ctx* ctx, const imdbn_rbm* r, const imdbn_chain* ch, int B) {
+    static const bool off = getenv("IMDBN_NO_CHAIN_TC") != nullptr;
+    if (off || ctx->precision != IMDBN_PREC_TF32 || !tc_shape_ok(r, B) || B < 512) return false;
+    if (tc_state(const_cast<imdbn_ctx*>(ctx))->encode == nullptr) return false;
+    if (ch->kind != IMDBN_CHAIN_NOISY_MF || ch->n_steps < 1 || ch->v_init || ch->sample_h || ch->sample_v) return false;
+    const int Dz = ch->clamp_suffix;
+    if (Dz <= 0 || Dz >= r->V || Dz > 512 || r->H > 256 || (r->H % 32) != 0) return false;
+    if (ch->mu && ch->Dz != Dz) return false;
+    for (int g = 0; g < r->ngroups; ++g)
+        if (r->group_start[g] < Dz) return false;          // softmax groups only inside the clamped block
+    return ct_smem_bytes((r->V + 31) / 32, r->H / 32) <= 227 * 1024;
+}
+
+// T / sigma / eta: DEVICE tables of n_steps entries each
+int tc_chain_t2i(imdbn_ctx* ctx, const imdbn_rbm* r, const imdbn_chain* ch, int B, float* v_out, const RngKey& key,
+                 const float* T, const float* sigma, const float* eta, cudaStream_t st) {
+    ChainTcArgs a{};
+    a.V = r->V; a.H = r->H; a.Dz = ch->clamp_suffix; a.B = B; a.n_steps = ch->n_steps;
+    a.kb_v = (r->V + 31) / 32; a.kb_h = r->H / 32;
+    a.mt_h = (r->H + 127) / 128; a.mt_v = (a.Dz + 127) / 128;
+    a.hb = r->hb; a.vb = r->vb; a.v_known = ch->v_known; a.mu = ch->mu;
+    a.T = T; a.sigma = sigma; a.eta = eta;
+    a.v_out = v_out; a.key = key; a.draw0 = ch->draw0;
+    const CUtensorMap* tUp = get_map(ctx, r->W, r->H, r->V, CT_BK, true);
+    const CUtensorMap* tDn = get_map(ctx, r->W, r->H, r->V, 128, false);
+    if (!tUp || !tDn) return fail(ctx, -5, "cuTensorMapEncodeTiled failed");
+    const size_t smem = ct_smem_bytes(a.kb_v, a.kb_h);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_chain_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    const int n_tiles = (B + CT_NC - 1) / CT_NC;
+    const int G = std::min(tc_sms(ctx), n_tiles);
+    k_chain_tc<<<G, CT_THREADS, smem, st>>>(*tUp, *tDn, a);
+    IMDBN_CHECK_LAUNCH(ctx, "k_chain_tc");
+    return 0;
+}
+
 // ---- SM partition (CUDA green contexts): two streams whose kernels run on disjoint sets of SMs ---------------
 namespace {
 struct SmPartition { bool tried = false; bool ok = false; CUstream big = nullptr, small_ = nullptr; int n_big = 0, n_small = 0; int want = 0; };

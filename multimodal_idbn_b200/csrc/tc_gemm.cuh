@@ -19,6 +19,10 @@ int tc_gemm_down(imdbn_ctx* ctx, const imdbn_rbm* r, const float* h, int B, floa
 int tc_gemm_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* vp, const float* hp,
                   const float* vn, const float* hn, int B, float* dS_out, const imdbn_update* upd,
                   cudaStream_t st);
+// TXT->IMG noisy mean-field chains as one persistent tcgen05 kernel (chain_tc.cuh); T / sigma / eta: device tables
+bool tc_chain_supported(const imdbn_ctx* ctx, const imdbn_rbm* r, const imdbn_chain* ch, int B);
+int tc_chain_t2i(imdbn_ctx* ctx, const imdbn_rbm* r, const imdbn_chain* ch, int B, float* v_out, const RngKey& key,
+                 const float* T, const float* sigma, const float* eta, cudaStream_t st);
 void tc_destroy(imdbn_ctx* ctx);
 // stream-K plan of a tensor-core pass producing M_total output features from K_total inputs
 SKPlan tc_plan(const imdbn_ctx* ctx, int M_total, int K_total, int B);

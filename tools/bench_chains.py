@@ -16,7 +16,7 @@ for B in [64, 4096, 65536]:
     vk2 = torch.zeros(B, V, device=dev); km2 = torch.zeros(B, V, device=dev); vk2[:, Dz:] = y; km2[:, Dz:] = 1
     mu = torch.rand(B, Dz, device=dev)
     for name, fn in [("cond_gibbs(50)", lambda: r.conditional_gibbs(vk, km, n_steps=50, clamp_prefix=Dz)),
-                     ("noisy_mf(50)", lambda: r.noisy_meanfield_annealed(vk2, km2, n_steps=50))]:
+                     ("noisy_mf(50)", lambda: r.noisy_meanfield_annealed(vk2, km2, n_steps=50, clamp_suffix=Dz))]:
         r._mu_pull = {"mu_k": mu, "eta0": 0.15} if name.startswith("noisy") else None
         fn(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
