@@ -216,6 +216,12 @@ k_chain_tc(const __grid_constant__ CUtensorMap tmUp, const __grid_constant__ CUt
                     const int iv = mt * 128 + quad * 32 + lane;
                     const bool free_unit = iv < a.Dz;
                     const float bi = free_unit ? a.vb[iv] : 0.0f;
+                    float mu_r[16];                      // all 16 mu-pull targets in flight before the arithmetic starts
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int r = row0 + grp * 16 + i;
+                        mu_r[i] = (a.mu && free_unit && r < a.B) ? __ldg(a.mu + (size_t)r * a.Dz + iv) : 0.0f;
+                    }
 #pragma unroll
                     for (int i = 0; i < 16; i += 2) {
                         const int c0 = grp * 16 + i;
@@ -232,8 +238,8 @@ k_chain_tc(const __grid_constant__ CUtensorMap tmUp, const __grid_constant__ CUt
                             float p0 = __fdividef(1.0f, 1.0f + __expf(-fmaf(n0, sig, (acc[i] + bi) * invT)));
                             float p1 = __fdividef(1.0f, 1.0f + __expf(-fmaf(n1, sig, (acc[i + 1] + bi) * invT)));
                             if (a.mu) {
-                                if (r0 < a.B) p0 = (1.0f - eta) * p0 + eta * a.mu[(size_t)r0 * a.Dz + iv];
-                                if (r1 < a.B) p1 = (1.0f - eta) * p1 + eta * a.mu[(size_t)r1 * a.Dz + iv];
+                                p0 = (1.0f - eta) * p0 + eta * mu_r[i];
+                                p1 = (1.0f - eta) * p1 + eta * mu_r[i + 1];
                             }
                             *reinterpret_cast<float*>(sV + ct_off(c0, iv)) = p0;
                             *reinterpret_cast<float*>(sV + ct_off(c0 + 1, iv)) = p1;
