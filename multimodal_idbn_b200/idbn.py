@@ -293,7 +293,9 @@ class iDBN:
         if loss_out is None and piped:
             # the upper layers write their losses from the side stream: use model-owned storage (a ring reused
             # every 8 steps) instead of a fresh allocation the caching allocator might recycle too early
-            ring = st.setdefault("loss_ring", torch.zeros(8, n, device=dev, dtype=torch.float32))
+            ring = st.get("loss_ring")
+            if ring is None:
+                ring = st["loss_ring"] = torch.zeros(8, n, device=dev, dtype=torch.float32)
             st["loss_pos"] = (st.get("loss_pos", -1) + 1) % 8
             loss_t = ring[st["loss_pos"]]
         elif loss_out is None:
