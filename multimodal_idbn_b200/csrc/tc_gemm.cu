@@ -126,6 +126,7 @@ struct StreamArgs {
     uint32_t tmem_cols;
     int nbuf;                              // TMEM accumulator sets (2 unless the batch tile is too wide)
     int stages;
+    int lo_tmem;                           // exact mode: W_lo tiles live in tensor memory (A operand from TMEM) behind the accumulators
     int blo;                               // exact mode: activation remainders are computed (0 = the caller knows them to be zero)
     const uint32_t* hint; uint32_t hint_gen;   // nullable: hint[0], hint[1] != hint_gen  =>  the activations of THIS pass were
                                            // found exactly representable by the operand-packing pass: take the blo = 0 layout
@@ -204,7 +205,8 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         blo_on = 0; n_stages = a.stages_x;
     }
     const int stage_bytes = ts_stage_bytes(a.Npad, SPLIT, blo_on != 0);
-    uint8_t* lo_base = smem + n_stages * stage_bytes;                 // [TS_NLO][TS_A_BYTES] (exact mode)
+    uint8_t* lo_base = smem + n_stages * stage_bytes;                 // [TS_NLO][TS_A_BYTES] (exact mode, W_lo in shared memory)
+    const uint32_t lo_col0 = (uint32_t)(a.nbuf * 2 * a.Npad);         // [TS_NLO][TS_BK columns] (exact mode, W_lo in tensor memory)
 
     auto load_A = [&](int it, int stage) {
         const int tile = it / k_iters, kit = it - tile * k_iters;
@@ -273,6 +275,7 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // ===================== MMA issuer (one thread) =====================
         if (elect_one()) {
             const uint32_t idesc = idesc_tf32(TS_BM, a.Npad, A_MN, false, false);
+            const uint32_t idesc_ts = idesc_tf32(TS_BM, a.Npad, false, false, false);     // A from tensor memory
             auto a_desc = [&](uint32_t sA, int g) -> uint64_t {
                 if (A_MN)   // k-group g = rows 8g..8g+7 (two 4-row swizzle atoms) of every column-block box
                     return smem_desc(sA + g * 1024, TS_BK * 128, 512, LAYOUT_SW128_BASE32B);
@@ -293,15 +296,23 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const uint32_t sA = smem_u32(smem + p_stage * stage_bytes);
                 const uint32_t sB = sA + TS_A_BYTES, sBlo = sB + (uint32_t)b_bytes;
                 const uint32_t sAlo = smem_u32(lo_base + l * TS_A_BYTES);
+                const uint32_t tAlo = tmem_base + lo_col0 + (uint32_t)(l * TS_BK);
                 const uint32_t blo = blo_on ? (blo_flags[p_stage * 4] | blo_flags[p_stage * 4 + 1] | blo_flags[p_stage * 4 + 2] |
                                               blo_flags[p_stage * 4 + 3]) : 0u;
                 // the remainder products (2^-11 of the main ones) have their own accumulator: added to the large
                 // running sum one by one they would each cost it a truncation
                 const uint32_t d_lo = p_tmem + (uint32_t)a.Npad;
-                if (!(a.dbg & 2) || p_first)
+                if (!(a.dbg & 2) || p_first) {
+                    if (a.lo_tmem) {
 #pragma unroll
-                for (int g = 0; g < TS_BK / 8; ++g)
-                    mma_tf32(d_lo, a_desc(sAlo, g), b_desc(sB, g), idesc, (p_first && g == 0) ? 0u : 1u);
+                        for (int g = 0; g < TS_BK / 8; ++g)
+                            mma_tf32_ts(d_lo, tAlo + g * 8, b_desc(sB, g), idesc_ts, (p_first && g == 0) ? 0u : 1u);
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < TS_BK / 8; ++g)
+                            mma_tf32(d_lo, a_desc(sAlo, g), b_desc(sB, g), idesc, (p_first && g == 0) ? 0u : 1u);
+                    }
+                }
                 if (blo && !(a.dbg & 2)) {
 #pragma unroll
                     for (int g = 0; g < TS_BK / 8; ++g) mma_tf32(d_lo, a_desc(sA, g), b_desc(sBlo, g), idesc, 1u);
@@ -398,8 +409,31 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             mbar_wait(&lo_empty[l], ((n / TS_NLO) & 1) ^ 1);
             bool nz = false;
             if (!(a.dbg & 1)) {
+                if (a.lo_tmem) {
+                    // thread <-> row m of the tile (the tensor-memory lane this warp may write): its 32 k values
+                    const int q = warp & 3, m = q * 32 + lane;
+                    const uint8_t* tile = smem + stage * stage_bytes;
+                    float x[32];
+                    if (A_MN) {      // [column block q][k][32 features], 32-byte swizzle atoms
+                        const uint8_t* col = tile + q * (TS_BK * 128) + (lane & 7) * 4;
 #pragma unroll
-                for (int i = 0; i < TS_A_BYTES / 16 / 128; ++i) sAlo[ct + i * 128] = tf32_lo4(sA[ct + i * 128]);
+                        for (int k = 0; k < 32; ++k)
+                            x[k] = tf32_lo(*reinterpret_cast<const float*>(col + k * 128 + (((lane >> 3) ^ (k & 3)) << 5)));
+                    } else {         // [row m][32 k], 16-byte swizzle chunks
+                        const uint8_t* row = tile + m * 128;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 v = tf32_lo4(*reinterpret_cast<const float4*>(row + ((j ^ (m & 7)) << 4)));
+                            x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w;
+                        }
+                    }
+                    tc_fence_after();
+                    tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + lo_col0 + (uint32_t)(l * TS_BK), x);
+                    tc_fence_before();
+                } else {
+#pragma unroll
+                    for (int i = 0; i < TS_A_BYTES / 16 / 128; ++i) sAlo[ct + i * 128] = tf32_lo4(sA[ct + i * 128]);
+                }
                 if (blo_on)
                 for (int i = ct; i < nB4; i += 128) {
                     const float4 lo = tf32_lo4(sB[i]);
@@ -522,22 +556,28 @@ static int stream_pass(imdbn_ctx* ctx, const imdbn_rbm* r, const float* act, int
     a.sk = tc_plan(ctx, M_total, K_total, B);
     a.total_iters = ((M_total + TS_BM - 1) / TS_BM) * a.sk.k_iters;
     a.part = part;
-    a.nbuf = (split ? 4 : 2) * a.Npad <= 512 ? 2 : 1;
-    a.tmem_cols = pow2_cols(a.nbuf * (split ? 2 : 1) * a.Npad);
+    // exact mode: the W_lo ring goes to tensor memory whenever the accumulators leave it TS_NLO x 32 columns
+    static const bool lo_smem_env = getenv("IMDBN_LO_SMEM") != nullptr;
+    a.lo_tmem = (split && !lo_smem_env && 2 * a.Npad + TS_NLO * 32 <= 512) ? 1 : 0;
+    const int ring_cols = a.lo_tmem ? TS_NLO * 32 : 0;
+    a.nbuf = (split ? 4 : 2) * a.Npad + ring_cols <= 512 ? 2 : 1;
+    a.tmem_cols = pow2_cols(a.nbuf * (split ? 2 : 1) * a.Npad + ring_cols);
     a.w_policy = l2_policy_for(r);
     a.w_stable = ctx->w_stable ? 1 : 0;
     a.blo = (split && !ctx->act_exact) ? 1 : 0;
     { static const int dbg_env = getenv("IMDBN_DEBUG_STREAM") ? atoi(getenv("IMDBN_DEBUG_STREAM")) : 0; a.dbg = dbg_env; }
     { static const int pf_env = getenv("IMDBN_L2_AHEAD") ? atoi(getenv("IMDBN_L2_AHEAD")) : 0; a.l2_ahead = pf_env * (64 / bk); }
-    const int budget = 226 * 1024 - TS_BAR_BYTES - (split ? TS_NLO * TS_BM * 32 * 4 : 0);
+    const int lo_ring_bytes = (split && !a.lo_tmem) ? TS_NLO * TS_BM * 32 * 4 : 0;
+    const int budget = 226 * 1024 - TS_BAR_BYTES - lo_ring_bytes;
     a.stages = std::max(2, std::min(split ? TS_MAX_STAGES : 4, budget / ts_stage_bytes(a.Npad, split, a.blo != 0)));
+    { static const int cap = getenv("IMDBN_TS_STAGES") ? atoi(getenv("IMDBN_TS_STAGES")) : 0; if (cap > 0) a.stages = std::max(2, std::min(a.stages, cap)); }
     a.stages_x = a.stages;
     if (a.blo && ctx->act_hint) {
         a.hint = ctx->act_hint; a.hint_gen = ctx->act_hint_gen;
         a.stages_x = std::max(2, std::min(TS_MAX_STAGES, budget / ts_stage_bytes(a.Npad, split, false)));
     }
     a.bar_off = std::max(a.stages * ts_stage_bytes(a.Npad, split, a.blo != 0), a.stages_x * ts_stage_bytes(a.Npad, split, false)) +
-                (split ? TS_NLO * TS_BM * 32 * 4 : 0);
+                lo_ring_bytes;
     const int G = tc_plan_ctas(a.sk, M_total);
     // W is [V, H] row-major: inner = H.  up: boxes [bk k-rows x 32 h]; down: boxes [128 v-rows x 32 h]
     const CUtensorMap* tmA = get_map(ctx, r->W, r->H, r->V, up ? bk : TS_BM, up);
@@ -558,7 +598,8 @@ static int stream_pass(imdbn_ctx* ctx, const imdbn_rbm* r, const float* act, int
     static const bool trace_on = getenv("IMDBN_TS_TRACE") != nullptr;
     static unsigned long long* trace_buf = nullptr;
     static int big_calls = 0;
-    const bool traced = trace_on && (size_t)r->V * r->H > (1u << 22) && ++big_calls >= 40 && big_calls <= 42;
+    static const int trace_from = trace_on ? std::max(40, atoi(getenv("IMDBN_TS_TRACE"))) : 0;     // (value = first traced call)
+    const bool traced = trace_on && (size_t)r->V * r->H > (1u << 22) && ++big_calls >= trace_from && big_calls <= trace_from + 2;
     if (traced) {
         if (!trace_buf) cudaMalloc((void**)&trace_buf, 148 * 8 * 8);
         cudaMemsetAsync(trace_buf, 0, 148 * 8 * 8, st);
