@@ -113,7 +113,7 @@ constexpr int TS_NGRP = 2;                 // converter groups of four warps, gr
 constexpr int TS_BAR_BYTES = 512;
 template <bool SPLIT> struct TsCfg {
     static constexpr int BK = SPLIT ? 32 : 64;          // reduction elements per pipeline stage
-    static constexpr int THREADS = SPLIT ? 448 : 192;   // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue, 6-13 converters
+    static constexpr int THREADS = SPLIT ? 192 + TS_NGRP * 128 : 192;   // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue, 6.. converters
     static constexpr int A_BYTES = TS_BM * BK * 4;
 };
 
@@ -126,14 +126,14 @@ struct StreamArgs {
     uint32_t tmem_cols;
     int nbuf;                              // TMEM accumulator sets (2 unless the batch tile is too wide)
     int stages;
-    int lo_tmem;                           // exact mode: W_lo tiles live in tensor memory (A operand from TMEM) behind the accumulators
+    int lo_tmem;                           // exact mode: 2 = the converters write W and W_lo into tensor memory behind the accumulators and both
+                                           // products take their A operand from there (the tensor core reads no weight from shared memory);
+                                           // 0 = W from shared memory, W_lo in a shared-memory ring (batch tiles too wide to leave TMEM room)
     int blo;                               // exact mode: activation remainders are computed (0 = the caller knows them to be zero)
     const uint32_t* hint; uint32_t hint_gen;   // nullable: hint[0], hint[1] != hint_gen  =>  the activations of THIS pass were
                                            // found exactly representable by the operand-packing pass: take the blo = 0 layout
     int stages_x;                          // ring depth of that layout
     int bar_off;                           // byte offset of the barrier block (behind the larger of the two layouts)
-    int dbg;                               // experiment switch (IMDBN_DEBUG_STREAM): 1 = converters idle, 2 = no lo products, 3 = both
-    int l2_ahead;                          // iterations whose W boxes are prefetched into L2 ahead of the ring (0 = off)
     int w_stable;                          // W is not written by any kernel still in flight: prefetch it before the wait
     uint64_t w_policy;                     // L2 eviction priority of the W stream
     unsigned long long* trace;             // nullable (IMDBN_TS_TRACE): [cta][8] globaltimer stamps
@@ -154,7 +154,7 @@ __device__ __forceinline__ float4 tf32_lo4(float4 x) {
     return make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
 }
 
-template <bool A_MN, bool SPLIT>
+template <bool A_MN, bool SPLIT, int LOM>
 __global__ void __launch_bounds__(TsCfg<SPLIT>::THREADS, 1)
 k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmB2, StreamArgs a) {
@@ -178,7 +178,17 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int b0 = blockIdx.y * a.Npad;          // batches wider than Npad rows: one chunk per blockIdx.y
     const int beg = sk_beg(a.sk, cta), end = sk_beg(a.sk, cta + 1);
     const int k_iters = a.sk.k_iters;
-#define TS_MARK(i) do { if (a.trace) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.trace[(blockIdx.x + gridDim.x * blockIdx.y) * 8 + (i)] = t_; } } while (0)
+#ifdef IMDBN_TS_TRACE_BUILD       // nvcc -DIMDBN_TS_TRACE_BUILD: per-CTA stage stamps and counts of the waits that found their
+                                  // barrier incomplete, for the launches selected by IMDBN_TS_TRACE=<first traced call>
+#define TS_MARK(i) do { if (a.trace) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.trace[(blockIdx.x + gridDim.x * blockIdx.y) * 16 + (i)] = t_; } } while (0)
+    int miss[3] = {0, 0, 0};
+#define TS_WAIT(slot, bar, par) do { if (a.trace && !mbar_test_wait(bar, par)) ++miss[slot]; mbar_wait(bar, par); } while (0)
+#define TS_MISS_FLUSH(slot0, n) do { if (a.trace) for (int i_ = 0; i_ < (n); ++i_) a.trace[(blockIdx.x + gridDim.x * blockIdx.y) * 16 + (slot0) + i_] = (unsigned long long)miss[i_]; } while (0)
+#else
+#define TS_MARK(i) do { } while (0)
+#define TS_WAIT(slot, bar, par) mbar_wait(bar, par)
+#define TS_MISS_FLUSH(slot0, n) do { } while (0)
+#endif
 
     // A kernel that may read W before its wait must not let ITS successors run ahead of a weight update either:
     // without w_stable the trigger follows the wait (the successor starts once everything before this kernel is done).
@@ -206,8 +216,15 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     const int stage_bytes = ts_stage_bytes(a.Npad, SPLIT, blo_on != 0);
     uint8_t* lo_base = smem + n_stages * stage_bytes;                 // [TS_NLO][TS_A_BYTES] (exact mode, W_lo in shared memory)
-    const uint32_t lo_col0 = (uint32_t)(a.nbuf * 2 * a.Npad);         // [TS_NLO][TS_BK columns] (exact mode, W_lo in tensor memory)
+    const uint32_t lo_col0 = (uint32_t)(a.nbuf * 2 * a.Npad);         // [TS_NLO][TS_BK columns] W_lo (lo_tmem 1) or [TS_NLO][W | W_lo] (2)
+    const uint32_t slot_cols = (uint32_t)(LOM == 2 ? 2 * TS_BK : TS_BK);
 
+    auto blo_any = [&](int st_) -> uint32_t {
+        uint32_t f = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) f |= blo_flags[st_ * 4 + i];
+        return f;
+    };
     auto load_A = [&](int it, int stage) {
         const int tile = it / k_iters, kit = it - tile * k_iters;
         const int m0 = tile * TS_BM, k0 = kit * TS_BK;
@@ -220,17 +237,6 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
             for (int j = 0; j < TS_BK / 32; ++j)
                 tma_load_2d_hint(sA + j * (TS_BM * 128), &tmA, k0 + j * 32, m0, &full[stage], a.w_policy);
-        }
-    };
-    auto prefetch_A = [&](int it) {
-        const int tile = it / k_iters, kit = it - tile * k_iters;
-        const int m0 = tile * TS_BM, k0 = kit * TS_BK;
-        if (A_MN) {
-#pragma unroll
-            for (int cb = 0; cb < TS_BM / 32; ++cb) tma_prefetch_l2_2d(&tmA, m0 + cb * 32, k0);
-        } else {
-#pragma unroll
-            for (int j = 0; j < TS_BK / 32; ++j) tma_prefetch_l2_2d(&tmA, k0 + j * 32, m0);
         }
     };
     auto load_B = [&](int it, int stage) {
@@ -250,9 +256,6 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (elect_one()) {
             const uint32_t tx = (uint32_t)(TS_A_BYTES + b_bytes);
             int pre = 0;
-            // L2 prefetch is a hint on a coherent cache: safe even while an earlier kernel still writes W
-            const int pf0 = min(end - beg, n_stages + a.l2_ahead);
-            if (a.l2_ahead > 0) for (int i = a.w_stable ? n_stages : 0; i < pf0; ++i) prefetch_A(beg + i);
             if (a.w_stable) {            // the weights of the first ring of stages stream in while the predecessor ends
                 pre = min(n_stages, end - beg);
                 for (int i = 0; i < pre; ++i) { mbar_expect_tx(&full[i], tx); load_A(beg + i, i); }
@@ -261,15 +264,15 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             TS_MARK(1);
             int stage = 0; uint32_t phase = 0;
             for (int it = beg; it < end; ++it) {
-                if (a.l2_ahead > 0 && it + n_stages + a.l2_ahead < end) prefetch_A(it + n_stages + a.l2_ahead);
                 if (it - beg >= pre) {
-                    mbar_wait(&empty[stage], phase ^ 1);
+                    TS_WAIT(0, &empty[stage], phase ^ 1);
                     mbar_expect_tx(&full[stage], tx);
                     load_A(it, stage);
                 }
                 load_B(it, stage);
                 if (++stage == n_stages) { stage = 0; phase ^= 1; }
             }
+            TS_MISS_FLUSH(8, 1);
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread) =====================
@@ -291,19 +294,18 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             int p_stage = -1, p_n = 0, p_buf = 0; bool p_last = false, p_first = false; uint32_t p_tmem = 0;
             auto issue_lo = [&]() {
                 const int l = p_n & (TS_NLO - 1);
-                mbar_wait(&lo_full[l], (p_n / TS_NLO) & 1);
+                TS_WAIT(1, &lo_full[l], (p_n / TS_NLO) & 1);
                 tc_fence_after();
                 const uint32_t sA = smem_u32(smem + p_stage * stage_bytes);
                 const uint32_t sB = sA + TS_A_BYTES, sBlo = sB + (uint32_t)b_bytes;
                 const uint32_t sAlo = smem_u32(lo_base + l * TS_A_BYTES);
-                const uint32_t tAlo = tmem_base + lo_col0 + (uint32_t)(l * TS_BK);
-                const uint32_t blo = blo_on ? (blo_flags[p_stage * 4] | blo_flags[p_stage * 4 + 1] | blo_flags[p_stage * 4 + 2] |
-                                              blo_flags[p_stage * 4 + 3]) : 0u;
+                const uint32_t tAlo = tmem_base + lo_col0 + (uint32_t)l * slot_cols;
+                const uint32_t blo = blo_on ? (blo_any(p_stage)) : 0u;
                 // the remainder products (2^-11 of the main ones) have their own accumulator: added to the large
                 // running sum one by one they would each cost it a truncation
                 const uint32_t d_lo = p_tmem + (uint32_t)a.Npad;
-                if (!(a.dbg & 2) || p_first) {
-                    if (a.lo_tmem) {
+                {
+                    if (LOM != 0) {
 #pragma unroll
                         for (int g = 0; g < TS_BK / 8; ++g)
                             mma_tf32_ts(d_lo, tAlo + g * 8, b_desc(sB, g), idesc_ts, (p_first && g == 0) ? 0u : 1u);
@@ -313,7 +315,7 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             mma_tf32(d_lo, a_desc(sAlo, g), b_desc(sB, g), idesc, (p_first && g == 0) ? 0u : 1u);
                     }
                 }
-                if (blo && !(a.dbg & 2)) {
+                if (blo) {
 #pragma unroll
                     for (int g = 0; g < TS_BK / 8; ++g) mma_tf32(d_lo, a_desc(sA, g), b_desc(sBlo, g), idesc, 1u);
                 }
@@ -333,11 +335,34 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * (SPLIT ? 2 : 1) * a.Npad);
                 for (int i = 0; i < n_it; ++i, ++n) {
-                    mbar_wait(&full[stage], phase);
+                    TS_WAIT(0, &full[stage], phase);
                     if (cur == beg && i == 0) TS_MARK(2);
                     tc_fence_after();
                     const uint32_t sA = smem_u32(smem + stage * stage_bytes);
                     const uint32_t sB = sA + TS_A_BYTES;
+                    if (SPLIT && LOM == 2) {
+                        // both weight terms come from tensor memory, written by the converters: no deferral
+                        const int l = n & (TS_NLO - 1);
+                        TS_WAIT(1, &lo_full[l], (n / TS_NLO) & 1);
+                        tc_fence_after();
+                        const uint32_t tA = tmem_base + lo_col0 + (uint32_t)l * slot_cols;
+                        const uint32_t d_lo = d_tmem + (uint32_t)a.Npad;
+#pragma unroll
+                        for (int g = 0; g < TS_BK / 8; ++g)
+                            mma_tf32_ts(d_tmem, tA + g * 8, b_desc(sB, g), idesc_ts, (i | g) != 0);
+#pragma unroll
+                        for (int g = 0; g < TS_BK / 8; ++g)
+                            mma_tf32_ts(d_lo, tA + TS_BK + g * 8, b_desc(sB, g), idesc_ts, (i | g) != 0);
+                        if (blo_on && blo_any(stage)) {
+                            const uint32_t sBlo = sB + (uint32_t)b_bytes;
+#pragma unroll
+                            for (int g = 0; g < TS_BK / 8; ++g) mma_tf32_ts(d_lo, tA + g * 8, b_desc(sBlo, g), idesc_ts, 1u);
+                        }
+                        { mma_commit(&empty[stage]); mma_commit(&lo_empty[l]); }
+                        if (i == n_it - 1) mma_commit(&acc_full[buf]);
+                        if (++stage == n_stages) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
 #pragma unroll
                     for (int g = 0; g < TS_BK / 8; ++g)         // one MMA per 8 k (tf32 UMMA_K)
                         mma_tf32(d_tmem, a_desc(sA, g), b_desc(sB, g), idesc, (i | g) != 0);
@@ -354,6 +379,7 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             if (SPLIT && p_stage >= 0) issue_lo();
             TS_MARK(3);
+            TS_MISS_FLUSH(9, 2);
         }
     } else if (warp < 6) {
         // ===================== epilogue: TMEM -> partial slab =====================
@@ -405,11 +431,11 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const float4* sB = reinterpret_cast<const float4*>(smem + stage * stage_bytes + TS_A_BYTES);
             float4* sBlo = reinterpret_cast<float4*>(smem + stage * stage_bytes + TS_A_BYTES + b_bytes);
             float4* sAlo = reinterpret_cast<float4*>(lo_base + l * TS_A_BYTES);
-            mbar_wait(&full[stage], phase);
-            mbar_wait(&lo_empty[l], ((n / TS_NLO) & 1) ^ 1);
+            TS_WAIT(0, &full[stage], phase);
+            TS_WAIT(1, &lo_empty[l], ((n / TS_NLO) & 1) ^ 1);
             bool nz = false;
-            if (!(a.dbg & 1)) {
-                if (a.lo_tmem) {
+            {
+                if (LOM != 0) {
                     // thread <-> row m of the tile (the tensor-memory lane this warp may write): its 32 k values
                     const int q = warp & 3, m = q * 32 + lane;
                     const uint8_t* tile = smem + stage * stage_bytes;
@@ -418,17 +444,21 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         const uint8_t* col = tile + q * (TS_BK * 128) + (lane & 7) * 4;
 #pragma unroll
                         for (int k = 0; k < 32; ++k)
-                            x[k] = tf32_lo(*reinterpret_cast<const float*>(col + k * 128 + (((lane >> 3) ^ (k & 3)) << 5)));
+                            x[k] = *reinterpret_cast<const float*>(col + k * 128 + (((lane >> 3) ^ (k & 3)) << 5));
                     } else {         // [row m][32 k], 16-byte swizzle chunks
                         const uint8_t* row = tile + m * 128;
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const float4 v = tf32_lo4(*reinterpret_cast<const float4*>(row + ((j ^ (m & 7)) << 4)));
+                            const float4 v = *reinterpret_cast<const float4*>(row + ((j ^ (m & 7)) << 4));
                             x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w;
                         }
                     }
                     tc_fence_after();
-                    tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + lo_col0 + (uint32_t)(l * TS_BK), x);
+                    const uint32_t tslot = tmem_base + ((uint32_t)(q * 32) << 16) + lo_col0 + (uint32_t)l * slot_cols;
+                    if (LOM == 2) tmem_st32_nowait(tslot, x);      // the word as it is: the tensor core reads its top 19 bits
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) x[k] = tf32_lo(x[k]);
+                    tmem_st32(tslot + (LOM == 2 ? TS_BK : 0), x);
                     tc_fence_before();
                 } else {
 #pragma unroll
@@ -441,17 +471,20 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     sBlo[i] = lo;
                 }
             }
-            nz = __any_sync(0xffffffffu, nz);
-            if (lane == 0) blo_flags[stage * 4 + cw] = nz ? 1u : 0u;
-            if (!(a.dbg & 4)) fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's smem reads
+            if (blo_on || LOM == 0) {
+                nz = __any_sync(0xffffffffu, nz);
+                if (lane == 0) blo_flags[stage * 4 + cw] = nz ? 1u : 0u;
+                fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's smem reads
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(&lo_full[l]);
         }
+        if (warp == 6 && lane == 0) TS_MISS_FLUSH(12, 2);
     }
 
     tc_fence_before();
     __syncthreads();
-    if (threadIdx.x == 0) TS_MARK(6);
+
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, a.tmem_cols);
@@ -528,16 +561,16 @@ int tc_plan_max_slabs(const SKPlan& p, int M_total) {
     return mx;
 }
 
-template <bool A_MN, bool SPLIT>
+template <bool A_MN, bool SPLIT, int LOM>
 static int launch_stream(imdbn_ctx* ctx, const CUtensorMap* tmA, const CUtensorMap* tmB, const CUtensorMap* tmB2,
                          StreamArgs& a, int G, int chunks, cudaStream_t st) {
     const size_t smem = (size_t)a.bar_off + TS_BAR_BYTES + 1024;
     static size_t smem_set = 0;          // the attribute is sticky: raise it only when a larger size is needed
     if (smem > smem_set) {
-        IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_tc_stream<A_MN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_tc_stream<A_MN, SPLIT, LOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
-    IMDBN_CUDA(ctx, launch_pdl(k_tc_stream<A_MN, SPLIT>, dim3(G, chunks), dim3(TsCfg<SPLIT>::THREADS), smem, st, *tmA, *tmB,
+    IMDBN_CUDA(ctx, launch_pdl(k_tc_stream<A_MN, SPLIT, LOM>, dim3(G, chunks), dim3(TsCfg<SPLIT>::THREADS), smem, st, *tmA, *tmB,
                                *tmB2, a));
     IMDBN_CHECK_LAUNCH(ctx, "k_tc_stream");
     return 0;
@@ -558,16 +591,14 @@ static int stream_pass(imdbn_ctx* ctx, const imdbn_rbm* r, const float* act, int
     a.part = part;
     // exact mode: the W_lo ring goes to tensor memory whenever the accumulators leave it TS_NLO x 32 columns
     static const bool lo_smem_env = getenv("IMDBN_LO_SMEM") != nullptr;
-    a.lo_tmem = (split && !lo_smem_env && 2 * a.Npad + TS_NLO * 32 <= 512) ? 1 : 0;
-    const int ring_cols = a.lo_tmem ? TS_NLO * 32 : 0;
+    a.lo_tmem = (split && !lo_smem_env && 2 * a.Npad + TS_NLO * 64 <= 512) ? 2 : 0;
+    const int ring_cols = a.lo_tmem * TS_NLO * 32;
     a.nbuf = (split ? 4 : 2) * a.Npad + ring_cols <= 512 ? 2 : 1;
     a.tmem_cols = pow2_cols(a.nbuf * (split ? 2 : 1) * a.Npad + ring_cols);
     a.w_policy = l2_policy_for(r);
     a.w_stable = ctx->w_stable ? 1 : 0;
     a.blo = (split && !ctx->act_exact) ? 1 : 0;
-    { static const int dbg_env = getenv("IMDBN_DEBUG_STREAM") ? atoi(getenv("IMDBN_DEBUG_STREAM")) : 0; a.dbg = dbg_env; }
-    { static const int pf_env = getenv("IMDBN_L2_AHEAD") ? atoi(getenv("IMDBN_L2_AHEAD")) : 0; a.l2_ahead = pf_env * (64 / bk); }
-    const int lo_ring_bytes = (split && !a.lo_tmem) ? TS_NLO * TS_BM * 32 * 4 : 0;
+    const int lo_ring_bytes = (split && a.lo_tmem == 0) ? TS_NLO * TS_BM * 32 * 4 : 0;
     const int budget = 226 * 1024 - TS_BAR_BYTES - lo_ring_bytes;
     a.stages = std::max(2, std::min(split ? TS_MAX_STAGES : 4, budget / ts_stage_bytes(a.Npad, split, a.blo != 0)));
     { static const int cap = getenv("IMDBN_TS_STAGES") ? atoi(getenv("IMDBN_TS_STAGES")) : 0; if (cap > 0) a.stages = std::max(2, std::min(a.stages, cap)); }
@@ -594,34 +625,49 @@ static int stream_pass(imdbn_ctx* ctx, const imdbn_rbm* r, const float* act, int
         tmB2 = tmB;
     }
     if (!tmA || !tmB || !tmB2) return fail(ctx, -5, "cuTensorMapEncodeTiled failed");
-    // IMDBN_TS_TRACE=1: per-CTA globaltimer stamps of one large-layer launch (debug aid)
+    // IMDBN_TS_TRACE=<n>: per-CTA globaltimer stamps of three large-layer launches from call n on (debug aid)
+#ifdef IMDBN_TS_TRACE_BUILD
     static const bool trace_on = getenv("IMDBN_TS_TRACE") != nullptr;
+#else
+    static const bool trace_on = false;      // (the kernel carries the stamps only when built with -DIMDBN_TS_TRACE_BUILD)
+#endif
     static unsigned long long* trace_buf = nullptr;
     static int big_calls = 0;
     static const int trace_from = trace_on ? std::max(40, atoi(getenv("IMDBN_TS_TRACE"))) : 0;     // (value = first traced call)
     const bool traced = trace_on && (size_t)r->V * r->H > (1u << 22) && ++big_calls >= trace_from && big_calls <= trace_from + 2;
     if (traced) {
-        if (!trace_buf) cudaMalloc((void**)&trace_buf, 148 * 8 * 8);
-        cudaMemsetAsync(trace_buf, 0, 148 * 8 * 8, st);
+        if (!trace_buf) cudaMalloc((void**)&trace_buf, 148 * 16 * 8);
+        cudaMemsetAsync(trace_buf, 0, 148 * 16 * 8, st);
         a.trace = trace_buf;
     }
     int rc;
-    if (split) rc = up ? launch_stream<true, true>(ctx, tmA, tmB, tmB2, a, G, chunks, st)
-                       : launch_stream<false, true>(ctx, tmA, tmB, tmB2, a, G, chunks, st);
-    else       rc = up ? launch_stream<true, false>(ctx, tmA, tmB, tmB2, a, G, chunks, st)
-                       : launch_stream<false, false>(ctx, tmA, tmB, tmB2, a, G, chunks, st);
+    if (split && a.lo_tmem == 2)
+               rc = up ? launch_stream<true, true, 2>(ctx, tmA, tmB, tmB2, a, G, chunks, st)
+                       : launch_stream<false, true, 2>(ctx, tmA, tmB, tmB2, a, G, chunks, st);
+    else if (split)
+               rc = up ? launch_stream<true, true, 0>(ctx, tmA, tmB, tmB2, a, G, chunks, st)
+                       : launch_stream<false, true, 0>(ctx, tmA, tmB, tmB2, a, G, chunks, st);
+    else       rc = up ? launch_stream<true, false, 0>(ctx, tmA, tmB, tmB2, a, G, chunks, st)
+                       : launch_stream<false, false, 0>(ctx, tmA, tmB, tmB2, a, G, chunks, st);
     if (traced && rc == 0) {
-        static unsigned long long h[148 * 8];
+        static unsigned long long h[148 * 16];
         cudaStreamSynchronize(st);
         cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
         unsigned long long t0 = ~0ull;
-        for (int c = 0; c < G; ++c) t0 = std::min(t0, h[c * 8]);
+        for (int c = 0; c < G; ++c) t0 = std::min(t0, h[c * 16]);
         const char* names[7] = {"entry", "after pdl_wait", "first stage full", "last mma issued", "epilogue seg0", "epilogue seg1", "exit"};
         fprintf(stderr, "k_tc_stream<%s> B=%d G=%d trace (ns after first CTA entry; min / mean / max over CTAs)\n", up ? "up" : "down", B, G);
-        for (int i = 0; i < 7; ++i) {
+        for (int i = 0; i < 6; ++i) {
             double mn = 1e18, mx = 0, sum = 0; int n = 0;
-            for (int c = 0; c < G; ++c) { if (!h[c * 8 + i]) continue; double v = (double)(h[c * 8 + i] - t0); mn = std::min(mn, v); mx = std::max(mx, v); sum += v; ++n; }
+            for (int c = 0; c < G; ++c) { if (!h[c * 16 + i]) continue; double v = (double)(h[c * 16 + i] - t0); mn = std::min(mn, v); mx = std::max(mx, v); sum += v; ++n; }
             if (n) fprintf(stderr, "  %-18s %8.0f %8.0f %8.0f  (n=%d)\n", names[i], mn, sum / n, mx, n);
+        }
+        const char* wn[5] = {"producer: empty", "mma: full", "mma: lo_full", "conv: full", "conv: lo_empty"};
+        const int slot_of[5] = {8, 9, 10, 12, 13};
+        for (int i = 0; i < 5; ++i) {       // waits that found their barrier incomplete (mean over CTAs; trace build only)
+            double sum = 0;
+            for (int c = 0; c < G; ++c) sum += (double)h[c * 16 + slot_of[i]];
+            fprintf(stderr, "  waits %-16s %6.1f\n", wn[i], sum / G);
         }
     }
     return rc;
