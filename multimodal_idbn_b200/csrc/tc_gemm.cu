@@ -721,7 +721,6 @@ int tc_gemm_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* vp, const flo
     a.n_tiles = (r->H + BN - 1) / BN;
     a.k_chunks = (B + ST_KC - 1) / ST_KC;
     if (upd) { a.lr = upd->lr; a.mom = upd->momentum; a.wd = upd->weight_decay; a.bsz = (float)upd->batch_global; }
-    { static const int dbg_env = getenv("IMDBN_DEBUG_STATS") ? atoi(getenv("IMDBN_DEBUG_STATS")) : 0; a.dbg = dbg_env; }
     const bool after_colstats = ctx->stats_after_colstats || ctx->colstats_job != nullptr;
     a.late_wait = after_colstats ? 1 : 0;
     ctx->stats_after_colstats = false;

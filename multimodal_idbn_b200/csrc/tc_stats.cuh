@@ -50,7 +50,6 @@ struct StatsArgs {
     const uint32_t* flags; uint32_t gen;          // flags[0] == gen: some v value is not exactly representable in tf32
     uint64_t w_policy, wm_policy;   // L2 eviction priorities of the W and W_m streams
     int late_wait;
-    int dbg;    // experiment switch (IMDBN_DEBUG_STATS): 1 = no operands/MMA, 2 = no W/W_m traffic
 };
 
 // ---- operand packing ------------------------------------------------------------------------------------------
@@ -328,7 +327,7 @@ k_tc_stats(const __grid_constant__ CUtensorMap tmVP, const __grid_constant__ CUt
 
     if (warp == 0) {
         // ===================== operand producer =====================
-        if (a.dbg != 1 && elect_one()) {
+        if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
             bool ext = false;
             if (PACK) {
@@ -376,7 +375,7 @@ k_tc_stats(const __grid_constant__ CUtensorMap tmVP, const __grid_constant__ CUt
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (a.dbg != 1 && elect_one()) {
+        if (elect_one()) {
             const uint32_t id_pos = idesc_tf32(ST_BM, ST_BN, true, true, false);
             const uint32_t id_neg = idesc_tf32(ST_BM, ST_BN, true, true, true);     // (-A) * B
             int stage = 0; uint32_t phase = 0;
@@ -422,7 +421,7 @@ k_tc_stats(const __grid_constant__ CUtensorMap tmVP, const __grid_constant__ CUt
         }
     } else if (warp == 2) {
         // ===================== IO producer: W / W_m quarter-tiles (128 rows x 32 columns) ============
-        if (UPDATE && a.dbg != 2 && a.dbg != 4 && elect_one()) {
+        if (UPDATE && elect_one()) {
             int hh = 0;
             for (int t = t_beg; t < t_end; t += t_step) {
                 const int m0 = (t / a.n_tiles) * ST_BM, n0 = (t % a.n_tiles) * ST_BN;
@@ -438,7 +437,7 @@ k_tc_stats(const __grid_constant__ CUtensorMap tmVP, const __grid_constant__ CUt
         }
     } else if (warp == 3) {
         // ===================== store issuer =====================
-        if (a.dbg != 2 && elect_one()) {
+        if (elect_one()) {
             int hh = 0;
             for (int t = t_beg; t < t_end; t += t_step) {
                 const int m0 = (t / a.n_tiles) * ST_BM, n0 = (t % a.n_tiles) * ST_BN;
@@ -446,22 +445,13 @@ k_tc_stats(const __grid_constant__ CUtensorMap tmVP, const __grid_constant__ CUt
                     const int s = hh & (ST_NSLOT - 1);
                     const uint8_t* slot = slots + s * ST_SLOT_BYTES;
                     mbar_wait(&io_written[s], (hh / ST_NSLOT) & 1);
-                    if (a.dbg != 3) {
-                        tma_store_2d_hint(&tmW, n0 + qt * 32, m0, slot, UPDATE ? a.w_policy : L2_EVICT_NORMAL);
-                        if (UPDATE) tma_store_2d_hint(&tmWm, n0 + qt * 32, m0, slot + ST_IO_BOX, a.wm_policy);
-                    }
+                    tma_store_2d_hint(&tmW, n0 + qt * 32, m0, slot, UPDATE ? a.w_policy : L2_EVICT_NORMAL);
+                    if (UPDATE) tma_store_2d_hint(&tmWm, n0 + qt * 32, m0, slot + ST_IO_BOX, a.wm_policy);
                     tma_store_commit();
-                    if (a.dbg == 5) {
-                        // keep one store in flight: release the PREVIOUS slot once its store has drained
-                        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                        if (hh > 0) mbar_arrive(&io_empty[(hh - 1) & (ST_NSLOT - 1)]);
-                    } else {
-                        tma_store_wait_read();        // shared memory of the slot may be overwritten
-                        mbar_arrive(&io_empty[s]);
-                    }
+                    tma_store_wait_read();            // shared memory of the slot may be overwritten
+                    mbar_arrive(&io_empty[s]);
                 }
             }
-            if (a.dbg == 5 && hh > 0) { tma_store_wait_read(); mbar_arrive(&io_empty[(hh - 1) & (ST_NSLOT - 1)]); }
             tma_store_wait_all();                     // global writes complete before the kernel ends
         }
     } else if (warp >= 4 && warp < 4 + ST_EPI_WARPS) {
@@ -475,7 +465,7 @@ k_tc_stats(const __grid_constant__ CUtensorMap tmVP, const __grid_constant__ CUt
         int seg = 0;
         for (int t = t_beg; t < t_end; t += t_step, ++seg) {
             const int buf = seg & 1;
-            if (a.dbg != 1) mbar_wait(&acc_full[buf], (seg >> 1) & 1);
+            mbar_wait(&acc_full[buf], (seg >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
             for (int qi = 0; qi < ST_SLICES / 2; ++qi) {
@@ -498,11 +488,9 @@ k_tc_stats(const __grid_constant__ CUtensorMap tmVP, const __grid_constant__ CUt
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&acc_empty[buf]);
                 }
-                if (a.dbg == 2) continue;
-                if (UPDATE && a.dbg != 4) mbar_wait(&io_full[s], (hh / ST_NSLOT) & 1);
+                if (UPDATE) mbar_wait(&io_full[s], (hh / ST_NSLOT) & 1);
                 else                      mbar_wait(&io_empty[s], ((hh / ST_NSLOT) & 1) ^ 1);
                 const float inv_bsz = 1.0f / a.bsz;
-                if (a.dbg != 6)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const uint32_t off = ((uint32_t)j ^ sw) << 4;

@@ -77,6 +77,51 @@ __global__ void k_pieces(float* __restrict__ W, float* __restrict__ M, int V, in
     }
 }
 
+// thread = tile row (the mapping the tensor-memory accumulator imposes on the update kernel's epilogue): 8 warps,
+// warp w owns rows 32*(w&3)+lane and the 32-column quarters (w>>2) and (w>>2)+2; PF = quarters loaded ahead
+template <int PF>
+__global__ void __launch_bounds__(256, 1) k_rows(float* __restrict__ W, float* __restrict__ M, int V, int H, float mom, float lr) {
+    const int tr = (V + 127) / 128, tc = (H + 127) / 128, nt = tr * tc;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = (warp & 3) * 32 + lane, grp = warp >> 2;
+    float4 w[PF + 1][8], m[PF + 1][8];
+    auto addr = [&](int i, int& r, int& c) {            // i-th quarter of this thread's sequence
+        const int t = blockIdx.x + (i >> 1) * gridDim.x;
+        r = (t / tc) * 128 + row; c = (t % tc) * 128 + (grp + 2 * (i & 1)) * 32;
+        return t < nt;
+    };
+    auto load = [&](int i, int b) {
+        int r, c;
+        if (!addr(i, r, c) || r >= V) return;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (c + 4 * j < H) { w[b][j] = *(const float4*)(W + (size_t)r * H + c + 4 * j); m[b][j] = *(const float4*)(M + (size_t)r * H + c + 4 * j); }
+    };
+#pragma unroll
+    for (int i = 0; i < PF; ++i) load(i, i);
+    for (int i = 0;; ++i) {
+        int r, c;
+        if (!addr(i, r, c)) break;
+#pragma unroll
+        for (int b = 0; b <= PF; ++b) {
+            if (i % (PF + 1) != b) continue;
+            if (PF > 0) {
+#pragma unroll
+                for (int b2 = 0; b2 <= PF; ++b2) if ((i + PF) % (PF + 1) == b2) load(i + PF, b2);
+            } else load(i, b);
+            if (r < V)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (c + 4 * j >= H) continue;
+                float4 ww = w[b][j], mm = m[b][j];
+                mm.x = mom * mm.x - lr * ww.x; mm.y = mom * mm.y - lr * ww.y; mm.z = mom * mm.z - lr * ww.z; mm.w = mom * mm.w - lr * ww.w;
+                ww.x += mm.x; ww.y += mm.y; ww.z += mm.z; ww.w += mm.w;
+                *(float4*)(W + (size_t)r * H + c + 4 * j) = ww; *(float4*)(M + (size_t)r * H + c + 4 * j) = mm;
+            }
+        }
+    }
+}
+
 __global__ void k_copy(const float4* __restrict__ a, float4* __restrict__ b, size_t n4) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) b[i] = a[i];
 }
@@ -116,6 +161,12 @@ int main() {
         snprintf(nm, 64, "pieces 32x128 g=%d", g); run(nm, [&] { k_pieces<32, 128><<<g, 256>>>(W, M, V, H, 0.5f, 1e-3f); }, B);
         snprintf(nm, 64, "pieces 64x128 g=%d", g); run(nm, [&] { k_pieces<64, 128><<<g, 256>>>(W, M, V, H, 0.5f, 1e-3f); }, B);
         snprintf(nm, 64, "pieces 128x128 g=%d", g); run(nm, [&] { k_pieces<128, 128><<<g, 256>>>(W, M, V, H, 0.5f, 1e-3f); }, B);
+    }
+    for (int g : {132, 148, 296}) {
+        char nm[64];
+        snprintf(nm, 64, "rows pf0 g=%d", g); run(nm, [&] { k_rows<0><<<g, 256>>>(W, M, V, H, 0.5f, 1e-3f); }, B);
+        snprintf(nm, 64, "rows pf1 g=%d", g); run(nm, [&] { k_rows<1><<<g, 256>>>(W, M, V, H, 0.5f, 1e-3f); }, B);
+        snprintf(nm, 64, "rows pf2 g=%d", g); run(nm, [&] { k_rows<2><<<g, 256>>>(W, M, V, H, 0.5f, 1e-3f); }, B);
     }
     for (int g : {148 * 8, 148 * 16}) {
         char nm[64]; snprintf(nm, 64, "copy W->M g=%d", g);

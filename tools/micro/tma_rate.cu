@@ -101,6 +101,84 @@ __global__ void __launch_bounds__(128, 1) k_copy_tma(const __grid_constant__ CUt
     tma_store_wait_all();
 }
 
+// TMA copy with row-slices: a 16 KB piece = [32 rows x 128 floats] = four [32 x 32] swizzled boxes issued back to back
+// (512 contiguous bytes per weight row in flight at once instead of 128)
+template <int D, int LAG>
+__global__ void __launch_bounds__(128, 1) k_copy_tma_rows(const __grid_constant__ CUtensorMap tm, float* W, int V, int H) {
+    extern __shared__ uint8_t raw[];
+    uint8_t* sm = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t bars[16];
+    const int tr = (V + 127) / 128, tc = (H + 127) / 128, nt = tr * tc;
+    if (threadIdx.x == 0) { for (int i = 0; i < 16; ++i) mbar_init(&bars[i], 1); fence_barrier_init(); }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    int my = 0; for (int t = blockIdx.x; t < nt; t += gridDim.x) ++my;
+    const int N = my * 4;
+    for (int i = 0; i < N + LAG; ++i) {
+        if (i < N) {
+            if (i >= D) wait_read<D - LAG - 1>();
+            const int t = blockIdx.x + (i >> 2) * gridDim.x, p = i & 3;
+            mbar_expect_tx(&bars[i % D], 16384);
+            for (int cb = 0; cb < 4; ++cb)
+                tma_load_2d(sm + (i % D) * 16384 + cb * 4096, &tm, (t % tc) * 128 + 32 * cb, (t / tc) * 128 + 32 * p, &bars[i % D]);
+        }
+        const int j = i - LAG;
+        if (j >= 0 && j < N) {
+            mbar_wait(&bars[j % D], (j / D) & 1);
+            const int t = blockIdx.x + (j >> 2) * gridDim.x, p = j & 3;
+            for (int cb = 0; cb < 4; ++cb)
+                tma_store_2d(&tm, (t % tc) * 128 + 32 * cb, (t / tc) * 128 + 32 * p, sm + (j % D) * 16384 + cb * 4096);
+            tma_store_commit();
+        }
+    }
+    tma_store_wait_all();
+}
+
+// mixed copy: TMA loads into a ring of D swizzled 16 KB slots, NT consumer threads read each slot from shared memory
+// and write it back with coalesced 16-byte global stores (8 lanes per 128-byte row piece)
+template <int D, int NT>
+__global__ void __launch_bounds__(NT + 32, 1) k_copy_mixed(const __grid_constant__ CUtensorMap tm, float* W, int V, int H) {
+    extern __shared__ uint8_t raw[];
+    uint8_t* sm = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t full[16], empty[16];
+    const int tr = (V + 127) / 128, tc = (H + 127) / 128, nt = tr * tc;
+    if (threadIdx.x == 0) { for (int i = 0; i < 16; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], NT / 32); } fence_barrier_init(); }
+    __syncthreads();
+    int my = 0; for (int t = blockIdx.x; t < nt; t += gridDim.x) ++my;
+    const int N = my * 4;
+    if (threadIdx.x >= NT) {
+        if (threadIdx.x == NT)
+            for (int i = 0; i < N; ++i) {
+                if (i >= D) mbar_wait(&empty[i % D], ((i / D) - 1) & 1);
+                const int t = blockIdx.x + (i >> 2) * gridDim.x, p = i & 3;
+                mbar_expect_tx(&full[i % D], 16384);
+                tma_load_2d(sm + (i % D) * 16384, &tm, (t % tc) * 128 + 32 * p, (t / tc) * 128, &full[i % D]);
+            }
+        return;
+    }
+    const int ch = threadIdx.x & 7, rr = threadIdx.x >> 3;
+    constexpr int RPP = NT / 8;
+    for (int i = 0; i < N; ++i) {
+        const int t = blockIdx.x + (i >> 2) * gridDim.x, p = i & 3;
+        const int r0 = (t / tc) * 128, c = (t % tc) * 128 + 32 * p + ch * 4;
+        const uint8_t* slot = sm + (i % D) * 16384;
+        mbar_wait(&full[i % D], (i / D) & 1);
+        float4 v[128 / RPP];
+#pragma unroll
+        for (int u = 0; u < 128 / RPP; ++u) {
+            const int r = rr + RPP * u;
+            v[u] = *reinterpret_cast<const float4*>(slot + r * 128 + ((ch ^ (r & 7)) << 4));
+        }
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[i % D]);
+#pragma unroll
+        for (int u = 0; u < 128 / RPP; ++u) {
+            const int r = r0 + rr + RPP * u;
+            if (r < V && c < H) { v[u].x += 1.0f; *reinterpret_cast<float4*>(W + (size_t)r * H + c) = v[u]; }
+        }
+    }
+}
+
 // LSU path: 128 threads issue 16-byte cp.async (LDGSTS) into the 128B-swizzled slot layout; completion by
 // cp.async.mbarrier.arrive.noinc
 template <int D>
@@ -173,6 +251,33 @@ int main() {
     run("copy tma D8 lag4", k_copy_tma<8, 4>, m0);
     run("copy tma D12 lag6", k_copy_tma<12, 6>, m0);
     run("copy tma D12 lag8", k_copy_tma<12, 8>, m0);
+    {
+        CUtensorMap m2; cuuint32_t b2[2] = {32, 32};
+        if (enc(&m2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, W, dims, str, b2, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)) { printf("enc2 failed\n"); return 1; }
+        run("copy tma rows32 D8 lag4", k_copy_tma_rows<8, 4>, m2);
+        run("copy tma rows32 D12 lag6", k_copy_tma_rows<12, 6>, m2);
+        run("copy tma rows32 D12 lag8", k_copy_tma_rows<12, 8>, m2);
+    }
+    {
+        auto runm = [&](const char* name, auto kern, int nthr) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM);
+            float sum = 0;
+            for (int it = 0; it < 8; ++it) {
+                cudaMemsetAsync(flush, it, 256u << 20);
+                cudaEventRecord(e0); kern<<<G, nthr, SM>>>(m0, W, V, H); cudaEventRecord(e1); cudaEventSynchronize(e1);
+                float ms; cudaEventElapsedTime(&ms, e0, e1); if (it >= 2) sum += ms;
+            }
+            cudaError_t e = cudaGetLastError();
+            printf("%-34s %7.2f us  %6.0f GB/s (in+out) %s\n", name, sum / 6 * 1e3, 2 * n * 4.0 / (sum / 6 * 1e-3) / 1e9, e ? cudaGetErrorString(e) : "");
+        };
+        runm("copy mixed D8 128thr", k_copy_mixed<8, 128>, 160);
+        runm("copy mixed D12 128thr", k_copy_mixed<12, 128>, 160);
+        runm("copy mixed D8 256thr", k_copy_mixed<8, 256>, 288);
+        runm("copy mixed D12 256thr", k_copy_mixed<12, 256>, 288);
+        for (int g : {132, 296}) { G = g; char nm[64]; snprintf(nm, 64, "copy mixed D12 256thr g=%d", g); if (g == 296) { /* two CTAs per SM need half the ring */ } runm(nm, k_copy_mixed<12, 256>, 288); }
+        G = 148;
+    }
     run("load lsu D2", k_load_lsu<2>, m0); run("load lsu D4", k_load_lsu<4>, m0); run("load lsu D8", k_load_lsu<8>, m0);
     run("load lsu D12", k_load_lsu<12>, m0);
     G = 74;

@@ -27,4 +27,4 @@ for mode in ("tf32", "tf32x2"):
         tot, cnt = ctx.profile_read(kind, V, H)
         out[name] = round(tot / max(1, cnt) * 1e3, 1)
     ctx.profile(False)
-    print(mode, "B", B, "dbg", os.environ.get("IMDBN_DEBUG_STREAM"), os.environ.get("IMDBN_DEBUG_STATS"), out, flush=True)
+    print(mode, "B", B, out, flush=True)
