@@ -6,8 +6,8 @@ stay on the device until the end of the epoch, and the next minibatch is copied 
 side stream while the current one trains.  ``represent`` / ``reconstruct`` / ``decode`` are chains
 of up / down passes; ``save_model`` writes the reference's ``{"layers", "params"}`` pickle.
 
-W&B visualisation (PCA plots, probes: idbn.py:207-305) is out of scope; only the scalar loss is
-logged when a ``wandb_run`` is given.
+W&B visualisation (PCA plots: idbn.py:207-284) is out of scope; the scalar loss and the linear-probe
+accuracies of the monitored layers (idbn.py:286-305, ``probe_utils.py`` here) are logged when a ``wandb_run`` is given.
 """
 from __future__ import annotations
 
@@ -401,6 +401,18 @@ class iDBN:
                 self.loss_history.append(mean_loss)
                 if self.wandb_run:
                     self.wandb_run.log({"idbn/loss": mean_loss, "epoch": epoch})
+            # linear probes on the monitored layers (idbn.py:286-305): embeddings, binning and the probe itself run on
+            # the device (probe_utils.py here); the PCA figures of idbn.py:244-284 are rendering and not produced
+            if (self.wandb_run and self.val_loader is not None and self.features is not None
+                    and log_every_probe and epoch % log_every_probe == 0):
+                from .probe_utils import log_linear_probe
+                for layer_idx in self._layers_to_monitor():
+                    tag = self._layer_tag(layer_idx)
+                    try:
+                        log_linear_probe(self, epoch=epoch, n_bins=5, test_size=0.2, steps=1000, lr=1e-2, patience=20,
+                                         min_delta=0.0, upto_layer=layer_idx, layer_tag=tag)
+                    except Exception as e:       # (the reference logs and continues)
+                        self.wandb_run.log({f"warn/idbn_probe_error_{tag}": str(e)})
 
     # ------------------------------------------------------------------ inference chains
     @torch.no_grad()

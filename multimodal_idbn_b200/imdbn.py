@@ -323,6 +323,15 @@ class iMDBN(nn.Module):
                 self.metrics_history.append(rec)
                 if self.wandb_run:
                     self.wandb_run.log(rec)
+            # linear probes on the joint embeddings (imdbn.py:695-706), on the device
+            if (self.wandb_run and self.val_loader is not None and self.features is not None
+                    and log_every_probe and epoch % log_every_probe == 0):
+                from .probe_utils import log_joint_linear_probe
+                try:
+                    log_joint_linear_probe(self, epoch=epoch, n_bins=5, test_size=0.2, steps=1000, lr=1e-2,
+                                           patience=20, min_delta=0.0, metric_prefix="joint")
+                except Exception as e:
+                    self.wandb_run.log({"warn/joint_probe_error": str(e)})
             if epoch % max(1, int(log_every)) == 0:
                 self._log_snapshots(epoch)
         print("[iMDBN] joint training finished.")

@@ -748,6 +748,44 @@ def case_panel():
     save("panel", **out)
 
 
+def case_probe():
+    """probe_utils.py: quantile binning (:151-166), bin names (:169-177), stratified split (:170-189) and the linear probe
+    with early stopping (:195-263) run by the reference on seeded inputs; the probe's ``nn.Linear`` is drawn from the
+    torch generator seeded here (the drop-in creates its layer on the host in the same way)."""
+    import imdbn.utils.probe_utils as ref_probe
+    assert ref_probe.__file__.startswith(REF)
+    g = torch.Generator().manual_seed(77)
+    out = {}
+    # continuous feature, a discrete one with ties (forces the jitter on equal edges), and class labels
+    vals = {"cont": torch.rand(240, generator=g) * 7.0,
+            "ties": torch.randint(0, 3, (240,), generator=g).float(),
+            "labels": torch.randint(0, 8, (240,), generator=g).float()}
+    for key, v in vals.items():
+        y, edges = ref_probe.make_bin_labels(v.clone(), n_bins=5)
+        tr, te = ref_probe.stratified_split(y, test_size=0.2, rng_seed=42)
+        out[key + "_values"] = v.numpy()
+        out[key + "_bins"] = y.numpy()
+        out[key + "_edges"] = edges.numpy()
+        out[key + "_train_idx"] = np.asarray(tr, dtype=np.int64)
+        out[key + "_test_idx"] = np.asarray(te, dtype=np.int64)
+        out[key + "_names"] = np.asarray(ref_probe._format_bin_names(edges, precision=4))
+    # linear probe on embeddings whose first coordinates carry the class
+    N, D, C = 300, 24, 5
+    y = torch.randint(0, C, (N,), generator=g)
+    X = torch.randn(N, D, generator=g) * 0.7
+    X[torch.arange(N), y] += 2.0
+    tr, te = ref_probe.stratified_split(y, test_size=0.2, rng_seed=42)
+    torch.manual_seed(1234)
+    acc, y_true, y_pred = ref_probe.train_linear_classifier(X[tr].numpy(), y[tr].numpy(), X[te].numpy(), y[te].numpy(),
+                                                            device=torch.device("cpu"), n_classes=C, max_steps=300,
+                                                            lr=1e-2, weight_decay=0.0, patience=20, min_delta=0.0)
+    out.update(probe_X=X.numpy(), probe_y=y.numpy(), probe_train_idx=np.asarray(tr), probe_test_idx=np.asarray(te),
+               probe_acc=np.float64(acc), probe_y_true=np.asarray(y_true), probe_y_pred=np.asarray(y_pred),
+               probe_seed=np.int64(1234))
+    np.savez_compressed(os.path.join(HERE, "probe.npz"), **out)
+    print("probe.npz", len(out), "arrays, probe acc", acc)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)  # fixtures should not depend on the thread count of this machine
     case_passes()
@@ -762,3 +800,4 @@ if __name__ == "__main__":
     case_rbm_extra()
     case_finetune()
     case_panel()
+    case_probe()

@@ -5,6 +5,7 @@ and the five checks of the reference's own acceptance script test_extraction.py 
 Every test runs in both fp32-faithful modes."""
 import os
 import sys
+import types
 
 import numpy as np
 import pytest
@@ -257,3 +258,74 @@ def test_label_clamped_trajectory_vs_oracle(M, tmp_path, monkeypatch):
     close(z_traj, torch.stack(ref, 0), dict(rtol=1e-4, atol=1e-5))
     layers = [O.RBMState(T(g[f"l{i}_W"]), T(g[f"l{i}_hb"]), T(g[f"l{i}_vb"]), None, None, None) for i in range(2)]
     close(imgs[-1], O.idbn_decode(layers, ref[-1]), dict(rtol=1e-4, atol=1e-5))
+
+
+class _StimBase(torch.utils.data.Dataset):
+    """Stand-in for the reference's stimulus dataset: images, one-hot labels and the per-item feature lists that
+    iDBN.__init__ collects into ``features`` (idbn.py:130-146)."""
+
+    def __init__(self, x, y, cls):
+        self.x, self.y = x, y
+        self.labels = cls.tolist()
+        self.cumArea_list = (cls.float() * 3.0 + torch.arange(len(cls)) * 1e-3).tolist()
+        self.CH_list = (10.0 - cls.float() + torch.arange(len(cls)) * 1e-3).tolist()
+
+    def __len__(self):
+        return len(self.x)
+
+    def __getitem__(self, i):
+        return self.x[i], self.y[i]
+
+
+def test_linear_probes_run_on_the_device(M, tmp_path, monkeypatch):
+    """SURVEY 8f rank 4 (probe_utils.py:195-263, 344-510; idbn.py:286-305): embeddings, binning, the probe and the
+    PCA projection run on the GPU; the probe reproduces the reference's accuracy on the golden inputs; iDBN.train
+    logs the probe accuracies of the monitored layers through its wandb run."""
+    monkeypatch.chdir(tmp_path)
+    from multimodal_idbn_b200 import probe_utils as P
+    g = load_golden("probe")
+    X, y = T(g["probe_X"]).to(DEV), torch.from_numpy(np.array(g["probe_y"])).to(DEV)
+    tr, te = P.stratified_split(y, test_size=0.2, rng_seed=42)                    # device labels, host procedure
+    assert tr == np.array(g["probe_train_idx"]).tolist() and te == np.array(g["probe_test_idx"]).tolist()
+    torch.manual_seed(int(g["probe_seed"]))
+    acc, y_true, y_pred = P.train_linear_classifier(X[tr], y[tr], X[te], y[te], device=torch.device(DEV), n_classes=5,
+                                                    max_steps=300, lr=1e-2, patience=20)
+    assert y_true == np.array(g["probe_y_true"]).tolist()
+    assert abs(acc - float(g["probe_acc"])) <= 0.05          # (same init and data; GPU reductions differ in the last bits)
+    yb, edges = P.make_bin_labels(T(g["cont_values"]).to(DEV), n_bins=5)
+    assert yb.is_cuda and torch.equal(yb.cpu(), torch.from_numpy(np.array(g["cont_bins"])))
+    assert torch.allclose(edges.cpu(), T(g["cont_edges"]), atol=1e-6)
+    # PCA on the device against scikit-learn (sign of a component is arbitrary)
+    from sklearn.decomposition import PCA
+    Z, ratio = P.pca_project(X, 3)
+    ref = PCA(n_components=3).fit(X.cpu().numpy())
+    assert Z.is_cuda and np.allclose(np.abs(Z.cpu().numpy()), np.abs(ref.transform(X.cpu().numpy())), atol=2e-3)
+    assert np.allclose(ratio.cpu().numpy(), ref.explained_variance_ratio_, atol=1e-4)
+
+    # the orchestrators on a trained stack: 4 classes drawn as 4 distinct bar patterns
+    gen = torch.Generator().manual_seed(9)
+    cls = torch.randint(0, 4, (160,), generator=gen)
+    x = (torch.rand(160, 1, 8, 8, generator=gen) < 0.05).float()
+    for i, c in enumerate(cls.tolist()):
+        x[i, 0, 2 * c:2 * c + 2, :] = 1.0
+    yoh = torch.nn.functional.one_hot(cls, 4).float()
+    base = _StimBase(x, yoh, cls)
+    train = torch.utils.data.DataLoader(torch.utils.data.Subset(base, list(range(0, 120))), batch_size=8)
+    val = torch.utils.data.DataLoader(torch.utils.data.Subset(base, list(range(120, 160))), batch_size=8)
+    logged = []
+    run = types.SimpleNamespace(log=lambda d: logged.append(dict(d)))
+    torch.manual_seed(0)
+    m = M.iDBN([64, 32, 16], dict(PARAMS), train, val, torch.device(DEV), wandb_run=run)
+    assert m.features is not None and set(m.features) == {"Cumulative Area", "Convex Hull", "Labels"}
+    for i, l in enumerate(m.layers):
+        l.set_rng(3 + i, 0)
+    m.train(2, log_every_probe=1)
+    keys = {k for d in logged for k in d}
+    assert {"probe/layer1/labels/acc", "probe/layer2/labels/acc", "probe/layer2/cum_area/acc", "idbn/loss"} <= keys, keys
+    E, feats = P.compute_val_embeddings_and_features(m, upto_layer=1)
+    assert E.is_cuda and E.shape == (40, 32) and feats["labels"].is_cuda
+    out = P.log_linear_probe(m, epoch=5, steps=200, upto_layer=1, layer_tag="layer1")
+    assert set(out) == {"layer1/cum_area", "layer1/convex_hull", "layer1/labels"}
+    for rec in out.values():
+        assert 0.0 <= rec["acc"] <= 1.0 and rec["confusion"].shape == (5, 5) and len(rec["bin_names"]) == 5
+    assert out["layer1/labels"]["acc"] >= 0.6        # four classes with distinct patterns: well above chance (0.25)

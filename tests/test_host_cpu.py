@@ -232,3 +232,33 @@ def test_device_resident_dataset_and_loaders(tmp_path):
     ds = DeviceDataset(torch.from_numpy(imgs), torch.from_numpy(nums), "cpu")
     xb, yb = next(iter(DeviceLoader(ds, 5, flat=True)))
     assert xb.shape == (5, 100) and torch.equal(xb, ds.images[:5]) and xb.data_ptr() == ds.images.data_ptr()
+
+
+def test_probe_utils_binning_split_and_probe_match_the_reference():
+    """quantile binning, bin names, the stratified split and the early-stopped linear probe of
+    probe_utils.py reproduce what the unmodified reference returned on the same seeded inputs (tests/golden/probe.npz,
+    written by make_golden.case_probe).  Everything here runs on the CPU device; the GPU test covers the device path."""
+    import numpy as np
+    from multimodal_idbn_b200 import probe_utils as P
+    import imdbn.utils.probe_utils as alias
+    assert alias.log_linear_probe is P.log_linear_probe and alias.stratified_split is P.stratified_split
+    g = np.load(os.path.join(REPO, "tests", "golden", "probe.npz"))
+    for key in ("cont", "ties", "labels"):
+        v = torch.from_numpy(g[key + "_values"])
+        y, edges = P.make_bin_labels(v, n_bins=5)
+        assert torch.equal(y, torch.from_numpy(g[key + "_bins"]))
+        assert torch.equal(edges, torch.from_numpy(g[key + "_edges"]))
+        tr, te = P.stratified_split(y, test_size=0.2, rng_seed=42)
+        assert tr == g[key + "_train_idx"].tolist() and te == g[key + "_test_idx"].tolist()
+        assert P._format_bin_names(edges, precision=4) == g[key + "_names"].tolist()
+    X, y = torch.from_numpy(g["probe_X"]), torch.from_numpy(g["probe_y"])
+    tr, te = P.stratified_split(y, test_size=0.2, rng_seed=42)
+    assert tr == g["probe_train_idx"].tolist() and te == g["probe_test_idx"].tolist()
+    torch.manual_seed(int(g["probe_seed"]))
+    acc, y_true, y_pred = P.train_linear_classifier(X[tr], y[tr], X[te], y[te], device=torch.device("cpu"), n_classes=5,
+                                                    max_steps=300, lr=1e-2, weight_decay=0.0, patience=20, min_delta=0.0)
+    assert y_true == g["probe_y_true"].tolist()
+    assert y_pred == g["probe_y_pred"].tolist()            # same stopping step, same selected parameters
+    assert abs(acc - float(g["probe_acc"])) < 1e-7
+    cm = P.confusion_matrix(y_true, y_pred, 5)
+    assert int(cm.sum()) == len(y_true) and int(cm.diag().sum()) == round(acc * len(y_true))
