@@ -370,13 +370,13 @@ class iDBN:
         if auto:
             self.pipeline_layers = (self.device.type == "cuda" and len(self.layers) > 1 and _dist.state() is None)
         try:
-            self._train_epochs(epochs)
+            self._train_epochs(epochs, log_every_probe)
         finally:
             self.sync()
             if auto:
                 self.pipeline_layers = None
 
-    def _train_epochs(self, epochs: int) -> None:
+    def _train_epochs(self, epochs: int, log_every_probe: int = 10) -> None:
         def keep(step_losses):
             # pipelined layers: the losses live in a short ring written from the side stream -- copy them there
             sides = self.__dict__.get("_side_stream")
