@@ -129,6 +129,11 @@ inline bool vec_ok(int B, int N, const float* bias, const float* a, const float*
 int up_pass(imdbn_ctx* ctx, const imdbn_rbm* r, const float* v, int B, float T, float* p_out,
             float* s_out, const RngKey& key, uint32_t draw_u, const PassPlan& pl, float* part,
             cudaStream_t st, const float* v2 = nullptr, int B1 = 0) {
+    if (pl.sk.k_iters && !v2 && tc_pass_fusable(ctx, r, B, true)) {       // large batch: the pass kernel finishes itself
+        ProfScope prof(ctx, IMDBN_KERNEL_UP, r->V, r->H, st);
+        const FusedFinish f{r->hb, 1.0f / fmaxf(1e-6f, T), p_out, s_out, key, draw_u};
+        return tc_gemm_up(ctx, r, v, B, part, st, nullptr, 0, &f);
+    }
     int rc = gemm_up(ctx, r, v, B, pl, part, st, v2, B1);
     if (rc) return rc;
     if (vec_ok(B, r->H, r->hb, p_out, s_out, nullptr)) {
@@ -153,10 +158,15 @@ int down_pass(imdbn_ctx* ctx, const imdbn_rbm* r, const float* h, int B, float T
               float* logits_out, float* s_out, float* logits_tmp, const RngKey& key,
               uint32_t draw_u, uint32_t draw_cat, const PassPlan& pl, float* part,
               cudaStream_t st) {
-    int rc = gemm_down(ctx, r, h, B, pl, part, st);
-    if (rc) return rc;
     const Groups gr = make_groups(r);
     float* lg = logits_out ? logits_out : (gr.n ? logits_tmp : nullptr);
+    if (pl.sk.k_iters && !lg && tc_pass_fusable(ctx, r, B, false)) {
+        ProfScope prof(ctx, IMDBN_KERNEL_DOWN, r->V, r->H, st);
+        const FusedFinish f{r->vb, 1.0f / fmaxf(1e-6f, T), p_out, s_out, key, draw_u};
+        return tc_gemm_down(ctx, r, h, B, part, st, &f);
+    }
+    int rc = gemm_down(ctx, r, h, B, pl, part, st);
+    if (rc) return rc;
     if (vec_ok(B, r->V, r->vb, p_out, s_out, lg)) {
         const size_t quads = (size_t)B * (r->V / 4);
         ChainPost4 cp{};

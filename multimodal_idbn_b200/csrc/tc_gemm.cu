@@ -136,6 +136,9 @@ struct StreamArgs {
     int bar_off;                           // byte offset of the barrier block (behind the larger of the two layouts)
     int w_stable;                          // W is not written by any kernel still in flight: prefetch it before the wait
     uint64_t w_policy;                     // L2 eviction priority of the W stream
+    FusedFinish fin;                       // FUSE instantiation: the epilogue finishes the pass instead of storing partials;
+    int pchunks, pu_q, pu_r;               // its CTAs are persistent over (tile, batch chunk) units: unit u = tile * pchunks + chunk, CTA c
+                                           // takes pu_q (+1 for c < pu_r) consecutive units, so the epilogue of one overlaps the next one's products
     unsigned long long* trace;             // nullable (IMDBN_TS_TRACE): [cta][8] globaltimer stamps
 };
 
@@ -154,7 +157,7 @@ __device__ __forceinline__ float4 tf32_lo4(float4 x) {
     return make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
 }
 
-template <bool A_MN, bool SPLIT, int LOM>
+template <bool A_MN, bool SPLIT, int LOM, bool FUSE>
 __global__ void __launch_bounds__(TsCfg<SPLIT>::THREADS, 1)
 k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmB2, StreamArgs a) {
@@ -175,9 +178,12 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cta = blockIdx.x;
-    const int b0 = blockIdx.y * a.Npad;          // batches wider than Npad rows: one chunk per blockIdx.y
-    const int beg = sk_beg(a.sk, cta), end = sk_beg(a.sk, cta + 1);
     const int k_iters = a.sk.k_iters;
+    // iteration range of this CTA: a stream-K share of one batch chunk (blockIdx.y), or whole (tile, chunk) units
+    const int beg = FUSE ? (cta * a.pu_q + min(cta, a.pu_r)) * k_iters : sk_beg(a.sk, cta);
+    const int end = FUSE ? ((cta + 1) * a.pu_q + min(cta + 1, a.pu_r)) * k_iters : sk_beg(a.sk, cta + 1);
+    auto tile_of = [&](int unit) { return FUSE ? unit / a.pchunks : unit; };
+    auto b0_of = [&](int unit) { return FUSE ? (unit % a.pchunks) * a.Npad : (int)blockIdx.y * a.Npad; };
 #ifdef IMDBN_TS_TRACE_BUILD       // nvcc -DIMDBN_TS_TRACE_BUILD: per-CTA stage stamps and counts of the waits that found their
                                   // barrier incomplete, for the launches selected by IMDBN_TS_TRACE=<first traced call>
 #define TS_MARK(i) do { if (a.trace) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.trace[(blockIdx.x + gridDim.x * blockIdx.y) * 16 + (i)] = t_; } } while (0)
@@ -226,7 +232,7 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         return f;
     };
     auto load_A = [&](int it, int stage) {
-        const int tile = it / k_iters, kit = it - tile * k_iters;
+        const int unit = it / k_iters, kit = it - unit * k_iters, tile = tile_of(unit);
         const int m0 = tile * TS_BM, k0 = kit * TS_BK;
         uint8_t* sA = smem + stage * stage_bytes;
         if (A_MN) {          // W[k rows, 32 features] boxes: one per 32-feature column block
@@ -240,7 +246,7 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
     };
     auto load_B = [&](int it, int stage) {
-        const int tile = it / k_iters, kit = it - tile * k_iters;
+        const int unit = it / k_iters, kit = it - unit * k_iters, b0 = b0_of(unit);
         const int k0 = kit * TS_BK;
         uint8_t* sB = smem + stage * stage_bytes + TS_A_BYTES;
 #pragma unroll
@@ -386,15 +392,47 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int quad = warp & 3;                               // TMEM lane quadrant this warp may read
         int seg = 0;
         for (int cur = beg; cur < end; ++seg) {
-            const int tile = cur / k_iters, kit0 = cur - tile * k_iters;
+            const int unit = cur / k_iters, kit0 = cur - unit * k_iters, tile = tile_of(unit), b0 = b0_of(unit);
             const int n_it = min(end - cur, k_iters - kit0);
             const int buf = seg % a.nbuf;
-            const int slab = cta - sk_cta_of(a.sk, tile * k_iters);
+            const int slab = FUSE ? 0 : cta - sk_cta_of(a.sk, tile * k_iters);
             mbar_wait(&acc_full[buf], (seg / a.nbuf) & 1);
             tc_fence_after();
             const int m = tile * TS_BM + quad * 32 + lane;
             float* dst = a.part + ((size_t)slab * a.B + b0) * a.M_total + m;
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * (SPLIT ? 2 : 1) * a.Npad);
+            if (FUSE) {
+                // whole tile accumulated here: bias, temperature, sigmoid, Bernoulli sample -- thread = output feature m,
+                // registers = 16 batch rows.  One Philox call yields the uniforms of 4 neighbouring features of a row:
+                // lane q of each 4-lane group makes the calls of the rows i % 4 == q and the group exchanges them.
+                const FusedFinish& f = a.fin;
+                const bool m_ok = m < a.M_total;
+                const float bias = m_ok ? __ldg(f.bias + m) : 0.0f;
+                const uint32_t colq = (uint32_t)(m & ~3), q = (uint32_t)lane & 3u;
+                for (int c0 = 0; c0 < a.Npad; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(taddr + c0, v);
+                    float4 u[4];
+                    if (f.s_out) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) u[j] = rf_uniform4(f.key, f.draw_u, (uint32_t)(b0 + c0 + 4 * j) + q, colq);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float p = __fdividef(1.0f, 1.0f + __expf(-(__fadd_rn(v[i], bias) * f.invT)));
+                        const size_t o = (size_t)(b0 + c0 + i) * a.M_total + m;
+                        const bool ok = m_ok && b0 + c0 + i < a.B;
+                        if (f.s_out) {
+                            const int src = (lane & ~3) | (i & 3);
+                            const float ux = __shfl_sync(0xffffffffu, u[i >> 2].x, src), uy = __shfl_sync(0xffffffffu, u[i >> 2].y, src);
+                            const float uz = __shfl_sync(0xffffffffu, u[i >> 2].z, src), uw = __shfl_sync(0xffffffffu, u[i >> 2].w, src);
+                            const float un = (q & 2u) ? ((q & 1u) ? uw : uz) : ((q & 1u) ? uy : ux);
+                            if (ok) f.s_out[o] = (p > un) ? 1.0f : 0.0f;
+                        }
+                        if (ok && f.p_out) f.p_out[o] = p;
+                    }
+                }
+            } else
             for (int c0 = 0; c0 < a.Npad; c0 += 16) {
                 float v[16];
                 tmem_ld16(taddr + c0, v);
@@ -561,16 +599,16 @@ int tc_plan_max_slabs(const SKPlan& p, int M_total) {
     return mx;
 }
 
-template <bool A_MN, bool SPLIT, int LOM>
+template <bool A_MN, bool SPLIT, int LOM, bool FUSE = false>
 static int launch_stream(imdbn_ctx* ctx, const CUtensorMap* tmA, const CUtensorMap* tmB, const CUtensorMap* tmB2,
                          StreamArgs& a, int G, int chunks, cudaStream_t st) {
     const size_t smem = (size_t)a.bar_off + TS_BAR_BYTES + 1024;
     static size_t smem_set = 0;          // the attribute is sticky: raise it only when a larger size is needed
     if (smem > smem_set) {
-        IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_tc_stream<A_MN, SPLIT, LOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_tc_stream<A_MN, SPLIT, LOM, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
-    IMDBN_CUDA(ctx, launch_pdl(k_tc_stream<A_MN, SPLIT, LOM>, dim3(G, chunks), dim3(TsCfg<SPLIT>::THREADS), smem, st, *tmA, *tmB,
+    IMDBN_CUDA(ctx, launch_pdl(k_tc_stream<A_MN, SPLIT, LOM, FUSE>, dim3(G, chunks), dim3(TsCfg<SPLIT>::THREADS), smem, st, *tmA, *tmB,
                                *tmB2, a));
     IMDBN_CHECK_LAUNCH(ctx, "k_tc_stream");
     return 0;
@@ -578,7 +616,7 @@ static int launch_stream(imdbn_ctx* ctx, const CUtensorMap* tmA, const CUtensorM
 
 // act2 != nullptr: the batch is the virtual concatenation [act (B1 rows) ; act2 (B - B1 rows)]
 static int stream_pass(imdbn_ctx* ctx, const imdbn_rbm* r, const float* act, int B, float* part, bool up,
-                       cudaStream_t st, const float* act2 = nullptr, int B1 = 0) {
+                       cudaStream_t st, const float* act2 = nullptr, int B1 = 0, const FusedFinish* fin = nullptr) {
     const int M_total = up ? r->H : r->V, K_total = up ? r->V : r->H;
     if (!aligned16(act)) return fail(ctx, -1, "tc pass: activation pointer must be 16-byte aligned");
     const bool split = tc_split(ctx);
@@ -641,7 +679,16 @@ static int stream_pass(imdbn_ctx* ctx, const imdbn_rbm* r, const float* act, int
         a.trace = trace_buf;
     }
     int rc;
-    if (split && a.lo_tmem == 2)
+    if (fin) {
+        if (split || act2 || a.sk.r != 0 || a.sk.q != a.sk.k_iters)
+            return fail(ctx, -1, "tc pass: a fused finish needs whole tiles per CTA in the single-pass tf32 mode");
+        a.fin = *fin;
+        const int units = ((M_total + TS_BM - 1) / TS_BM) * chunks;          // (tile, batch chunk) pairs, whole K each
+        const int Gp = std::min(tc_sms(ctx), units);
+        a.pchunks = chunks; a.pu_q = units / Gp; a.pu_r = units % Gp;
+        rc = up ? launch_stream<true, false, 0, true>(ctx, tmA, tmB, tmB2, a, Gp, 1, st)
+                : launch_stream<false, false, 0, true>(ctx, tmA, tmB, tmB2, a, Gp, 1, st);
+    } else if (split && a.lo_tmem == 2)
                rc = up ? launch_stream<true, true, 2>(ctx, tmA, tmB, tmB2, a, G, chunks, st)
                        : launch_stream<false, true, 2>(ctx, tmA, tmB, tmB2, a, G, chunks, st);
     else if (split)
@@ -674,11 +721,18 @@ static int stream_pass(imdbn_ctx* ctx, const imdbn_rbm* r, const float* act, int
 }
 
 int tc_gemm_up(imdbn_ctx* ctx, const imdbn_rbm* r, const float* v, int B, float* part, cudaStream_t st,
-               const float* v2, int B1) {
-    return stream_pass(ctx, r, v, B, part, true, st, v2, B1);
+               const float* v2, int B1, const FusedFinish* fin) {
+    return stream_pass(ctx, r, v, B, part, true, st, v2, B1, fin);
 }
-int tc_gemm_down(imdbn_ctx* ctx, const imdbn_rbm* r, const float* h, int B, float* part, cudaStream_t st) {
-    return stream_pass(ctx, r, h, B, part, false, st);
+int tc_gemm_down(imdbn_ctx* ctx, const imdbn_rbm* r, const float* h, int B, float* part, cudaStream_t st,
+                 const FusedFinish* fin) {
+    return stream_pass(ctx, r, h, B, part, false, st, nullptr, 0, fin);
+}
+bool tc_pass_fusable(const imdbn_ctx* ctx, const imdbn_rbm* r, int B, bool up) {
+    static const bool off = getenv("IMDBN_NO_FUSED_FINISH") != nullptr;
+    if (off || !fast_math(ctx) || B <= 256 || !(up ? tc_up_supported(ctx, r, B) : tc_down_supported(ctx, r, B))) return false;
+    const SKPlan p = tc_plan(ctx, up ? r->H : r->V, up ? r->V : r->H, B);
+    return p.r == 0 && p.q == p.k_iters;
 }
 
 // tile shape: HBM-bound small batches stream W / W_m through 128 x 128 tiles with packed operands; from 512 rows the

@@ -12,10 +12,20 @@ size_t tc_ws_bytes(const imdbn_ctx* ctx, const imdbn_rbm* r, int B);
 // the statistics call for this shape packs its operands (and can take the column statistics along: ColstatsJob)
 bool tc_stats_packs(const imdbn_ctx* ctx, const imdbn_rbm* r, int B);
 
+// Finish of a pass done by the pass kernel's own epilogue (large batches, where every output tile is accumulated by
+// ONE CTA and the partial-slab round trip plus the finish kernel are pure overhead): bias, temperature, sigmoid and the
+// Bernoulli sample of rbm.py:92,110,125,175,203, the arithmetic and the random field of k_finish_up4 / k_finish_down4<true>.
+struct FusedFinish {
+    const float* bias; float invT; float* p_out; float* s_out; RngKey key; uint32_t draw_u;
+};
+// the pass of this shape accumulates whole tiles per CTA in the fast tensor-core mode: its finish can be fused
+bool tc_pass_fusable(const imdbn_ctx* ctx, const imdbn_rbm* r, int B, bool up);
+
 // v2 != nullptr: the batch is [v (B1 rows) ; v2 (B - B1 rows)] read from two matrices (B1 % 8 == 0, B <= 256)
 int tc_gemm_up(imdbn_ctx* ctx, const imdbn_rbm* r, const float* v, int B, float* part, cudaStream_t st,
-               const float* v2 = nullptr, int B1 = 0);
-int tc_gemm_down(imdbn_ctx* ctx, const imdbn_rbm* r, const float* h, int B, float* part, cudaStream_t st);
+               const float* v2 = nullptr, int B1 = 0, const FusedFinish* fin = nullptr);
+int tc_gemm_down(imdbn_ctx* ctx, const imdbn_rbm* r, const float* h, int B, float* part, cudaStream_t st,
+                 const FusedFinish* fin = nullptr);
 int tc_gemm_stats(imdbn_ctx* ctx, const imdbn_rbm* r, const float* vp, const float* hp,
                   const float* vn, const float* hn, int B, float* dS_out, const imdbn_update* upd,
                   cudaStream_t st);

@@ -5,6 +5,8 @@ CPU oracle.  Where the full oracle product would take minutes, the oracle is eva
 rows / columns (every output element is an independent dot product) and the rest is covered by a size-independent
 property: linearity in the batch (the sum of narrow-kernel results over 256-row slices equals the wide kernel's)."""
 import ctypes as C
+import os
+import sys
 
 import pytest
 import torch
@@ -14,6 +16,7 @@ from oracle.philox import RandomField
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SHAPES = [(10000, 4096), (4096, 2048), (2080, 1024)]
 
 
@@ -145,3 +148,40 @@ def test_cd_batch4096_vs_oracle(V, H, groups, k, prec):
                 assert dev_mean < 2e-2, dev_mean
     finally:
         M.set_precision("fp32")
+
+
+_FUSED_SNIPPET = r"""
+import hashlib, sys, torch
+sys.path.insert(0, %r)
+import multimodal_idbn_b200 as M
+M.set_precision("tf32")
+torch.manual_seed(3)
+r = M.RBM(4096, 2048, 0.1, 1e-4, 0.5).to("cuda")
+g = torch.Generator().manual_seed(4)
+v = (torch.rand(1000, 4096, generator=g) < 0.3).float().cuda()          # ragged last chunk (1000 = 3 x 256 + 232)
+h = torch.rand(1000, 2048, generator=g).cuda()
+r.set_rng(17, 0)
+outs = [r.forward(v), r.visible_probs(h), r.backward_sample(h), r.gibbs_step(v)[0], r.gibbs_step(v)[1]]
+loss = r.train_epoch(v, 0, 1, CD=2)
+outs += [loss.reshape(1), r.W.detach(), r.hid_bias.detach(), r.vis_bias.detach()]
+torch.cuda.synchronize()
+print("DIGEST", hashlib.sha256(b"".join(o.detach().cpu().numpy().tobytes() for o in outs)).hexdigest())
+"""
+
+
+def test_fused_pass_finish_is_bit_identical_to_the_finish_kernels():
+    """Large batches in tf32 mode: the pass kernel's own epilogue applies bias / temperature / sigmoid / Bernoulli
+    sampling (FusedFinish) instead of storing partial slabs for k_finish_up4 / k_finish_down4.  Same arithmetic, same
+    random field: probabilities, samples and a CD-2 update are bit-identical to the unfused path
+    (IMDBN_NO_FUSED_FINISH=1)."""
+    import subprocess
+    digests = []
+    for off in (False, True):
+        env = dict(os.environ)
+        env.pop("IMDBN_NO_FUSED_FINISH", None)
+        if off:
+            env["IMDBN_NO_FUSED_FINISH"] = "1"
+        out = subprocess.run([sys.executable, "-c", _FUSED_SNIPPET % REPO], env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        digests.append([l for l in out.stdout.splitlines() if l.startswith("DIGEST")][0])
+    assert digests[0] == digests[1]
