@@ -2,6 +2,8 @@
 // (M = 128, K = 8, N in {64, 128, 256}) from one thread, then commits and waits.  Operand contents are irrelevant.
 //   mode 0: A from shared memory, K-major SW128      mode 1: A from shared memory, MN-major (32-byte atoms)
 //   mode 2: A from tensor memory
+//   mode 3: A from shared memory, K-major, 32-byte swizzle (one 32-byte row per k-group: the tile of one MMA is 4 KB contiguous)
+//   mode 4: A from shared memory, K-major, 64-byte swizzle
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/micro/mma_rate tools/micro/mma_rate.cu
 #include <cstdio>
 #include <cstdint>
@@ -36,6 +38,8 @@ __global__ void __launch_bounds__(128, 1) k_rate(int mode, int N, int reps, int 
                     mma_tf32_ts(d, tm + 2 * N + (uint32_t)(g * 8), bd, idesc, 1u);
                 } else {
                     const uint64_t ad = mode == 1 ? smem_desc(sA + g * 1024, 64 * 128, 512, LAYOUT_SW128_BASE32B)
+                                      : mode == 3 ? smem_desc(sA + g * 4096, 16, 256, 6)                  // 8 rows x 32 B atoms
+                                      : mode == 4 ? smem_desc(sA + (g / 2) * 8192 + (g % 2) * 32, 16, 512, 4)   // 8 rows x 64 B atoms
                                                   : smem_desc(sA + (g / 4) * (128 * 128) + (g % 4) * 32, 16, 1024, LAYOUT_SW128);
                     mma_tf32(d, ad, bd, idesc, 1u);
                 }
@@ -58,7 +62,7 @@ int main() {
     CK(cudaFuncSetAttribute(k_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     const int reps = 200;
     for (int two = 0; two < 2; ++two)
-    for (int mode = 0; mode < 3; ++mode)
+    for (int mode = 0; mode < 5; ++mode)
         for (int N : {64, 128, 256}) {
             if (2 * N + 64 > 512 && mode == 2) continue;
             if (two && 2 * N > 512) continue;
@@ -67,7 +71,7 @@ int main() {
             long long h[296]; CK(cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost));
             double iss = 0, tot = 0; for (int i = 0; i < 148; ++i) { iss += h[2 * i]; tot += h[2 * i + 1]; }
             printf("mode %d (%s) N=%3d accumulators=%d: issue %.1f clk/MMA, issue+execute %.1f clk/MMA  (ideal %d)\n", mode,
-                   mode == 0 ? "A smem K-major" : mode == 1 ? "A smem MN-major" : "A tmem", N, two + 1, iss / 148 / (reps * 8),
+                   mode == 0 ? "A smem K-major SW128" : mode == 1 ? "A smem MN-major" : mode == 2 ? "A tmem" : mode == 3 ? "A smem K-major SW32" : "A smem K-major SW64", N, two + 1, iss / 148 / (reps * 8),
                    tot / 148 / (reps * 8), 128 * N * 8 / 2048);
         }
     return 0;
