@@ -87,6 +87,11 @@ int imdbn_set_precision(imdbn_ctx* ctx, int prec);
 int imdbn_set_sm_limit(imdbn_ctx* ctx, int n_sms);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t imdbn_launch_count(imdbn_ctx* ctx);
+/* Asynchronous copy on `stream` (cudaMemcpyAsync, direction inferred from the pointers).  No reference counterpart:
+ * the minibatch staging of iDBN.train (idbn.py:199-200, `.to(device)`) and the per-step read-back of the losses
+ * (idbn.py:202, `.item()` in the reference) go through this call, so that the host side of a training step -- within
+ * 10 % of the device side at batch 64 -- does not pay for a framework dispatch per copy. */
+int imdbn_copy_async(void* dst, const void* src, size_t bytes, imdbn_stream stream);
 
 /* ---- in-library kernel timing (bench.py's roofline leg) --------------------------------------
  * While enabled, the GEMM-shaped kernels and the chain kernel are bracketed by CUDA events recorded

@@ -78,6 +78,7 @@ SIGNATURES = {
     "imdbn_last_error": (C.c_char_p, [_P]),
     "imdbn_set_precision": (_I, [_P, _I]),
     "imdbn_launch_count": (C.c_int64, [_P]),
+    "imdbn_copy_async": (_I, [_P, _P, C.c_size_t, _P]),
     "imdbn_profile_enable": (_I, [_P, _I]),
     "imdbn_profile_read": (_I, [_P, _I, _I, _I, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "imdbn_up": (_I, [_P, C.POINTER(RbmStruct), _P, _I, _F, _P, _P, C.POINTER(RngStruct), _U, _P]),

@@ -646,7 +646,11 @@ int cd_core(imdbn_ctx* ctx, const imdbn_rbm* r, const float* data, int B, int k,
     if (tail && tail->pos_h_in) {
         // positive phase already computed together with the previous call's forward pass
         pos_h = const_cast<float*>(tail->pos_h_in);
-        k_bernoulli<<<ew_blocks(nBH, ctx->num_sms), 256, 0, st>>>(pos_h, B, H, h_s, key, 0);      // rbm.py:203
+        if (vec_ok(B, H, pos_h, h_s, nullptr, nullptr))                                               // rbm.py:203
+            IMDBN_CUDA(ctx, launch_pdl(k_bernoulli4, dim3(vec_blocks((size_t)B * (H / 4), ctx->num_sms)), dim3(256), 0, st,
+                                       (const float*)pos_h, B, H, h_s, key, 0u));
+        else
+            k_bernoulli<<<ew_blocks(nBH, ctx->num_sms), 256, 0, st>>>(pos_h, B, H, h_s, key, 0);
         IMDBN_CHECK_LAUNCH(ctx, "k_bernoulli");
     } else {
         rc = up_pass(ctx, r, data, B, 1.0f, pos_h, h_s, key, 0, pu, part, st);      // rbm.py:199,203
@@ -888,6 +892,11 @@ int imdbn_set_precision(imdbn_ctx* ctx, int prec) {
 }
 
 int64_t imdbn_launch_count(imdbn_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int imdbn_copy_async(void* dst, const void* src, size_t bytes, imdbn_stream stream) {
+    if (!dst || !src) return -1;
+    return (int)cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream);
+}
 
 int imdbn_profile_enable(imdbn_ctx* ctx, int enable) {
     IMDBN_ARG(ctx, ctx != nullptr);

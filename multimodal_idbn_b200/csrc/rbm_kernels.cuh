@@ -80,6 +80,23 @@ __global__ void k_bernoulli(const float* __restrict__ p, int B, int V, float* __
     }
 }
 
+// The same on four columns per thread (one Philox call), launched as a programmatic dependent: the wait comes first
+// and the trigger after it, so whatever is launched behind this kernel still starts only once everything before it
+// has completed (the CD passes that follow prefetch W before their own wait).  V % 4 == 0, 16-byte aligned rows.
+__global__ void __launch_bounds__(256) k_bernoulli4(const float* __restrict__ p, int B, int V, float* __restrict__ s_out,
+                                                    RngKey key, uint32_t draw_u) {
+    pdl_wait();
+    pdl_trigger();
+    const unsigned q_per_row = (unsigned)V >> 2, total = (unsigned)B * q_per_row;
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const unsigned b = idx / q_per_row, c = (idx - b * q_per_row) << 2;
+        const float4 x = *reinterpret_cast<const float4*>(p + (size_t)b * V + c);
+        const float4 u = rf_uniform4(key, draw_u, b, c);
+        *reinterpret_cast<float4*>(s_out + (size_t)b * V + c) =
+            make_float4(x.x > u.x ? 1.0f : 0.0f, x.y > u.y ? 1.0f : 0.0f, x.z > u.z ? 1.0f : 0.0f, x.w > u.w ? 1.0f : 0.0f);
+    }
+}
+
 // One warp per (row, group): softmax of the logits over [s,e) written over p (rbm.py:113-114) and,
 // if s_out, the one-hot categorical draw of sample_visible (rbm.py:129-133): q = clamp(p,1e-8,1),
 // q /= sum q, idx = #{j: cdf_j <= u} with a sequential fp32 cdf (oracle.categorical_index).
