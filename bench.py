@@ -302,18 +302,18 @@ def run_ours(args):
         model.sync()
         return t_enq
 
-    # K steps, three times; the MEDIAN repetition is reported (this loop includes the host: a single repetition
-    # is exposed to scheduling noise of the box), all three are listed in e2e.runs_ms
+    # K steps, five times; the MEDIAN repetition is reported (this loop includes the host: a single repetition
+    # is exposed to scheduling noise of the box), all five are listed in e2e.runs_ms
     e2e_loop(warm, 0)
     e2e_runs, e2e_host = [], []
-    for _ in range(3):
+    for _ in range(5):
         barrier()
         t0 = time.perf_counter()
         t_enq = e2e_loop(steps, warm)
         barrier()
         e2e_runs.append(max_over_ranks((time.perf_counter() - t0) * 1e3))
         e2e_host.append((t_enq - t0) * 1e3)
-    e2e_ms = sorted(e2e_runs)[1]
+    e2e_ms = sorted(e2e_runs)[2]
     e2e_val = world * BATCH * steps / (e2e_ms * 1e-3)
     assert torch.isfinite(loss_host[warm:]).all()
 
@@ -398,7 +398,7 @@ def run_ours(args):
                    "l2": "state (W, W_m of both layers: 252 MB) + 164 MB of rotating inputs exceed the "
                          "126 MB L2; no explicit flush"},
         "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": e2e_ms / steps, "runs_ms": e2e_runs,
-                "host_enqueue_ms_per_step": sorted(e2e_host)[1] / steps,      # host time to enqueue the loop (rank 0)
+                "host_enqueue_ms_per_step": sorted(e2e_host)[2] / steps,      # host time to enqueue the loop (rank 0)
                 "h2d_bytes_per_step": BATCH * LAYERS[0] * 4, "d2h_bytes_per_step": 4 * len(LAYERS[1:]),
                 "d2h": "per-layer losses of every step: one 8-byte device-to-host copy per step on the upper layers' stream into pinned host memory"},
         "gpu_launches": launches,

@@ -20,16 +20,19 @@ __device__ __forceinline__ float div_t(float x, float T, float invT) { return FA
 
 // The loads of up to 16 slabs are issued together (one L2 round trip instead of one per group of four -- the finish
 // sits on the critical path between two passes); the additions stay in slab order.
+// (W = loads in flight: 16 for the up pass, whose few output tiles are split over many CTAs; 4 for the down pass, whose
+// tiles have at most three slabs and whose finish carries the chain epilogue -- 16 there meant register spills.)
+template <int W = 16>
 __device__ __forceinline__ float4 sum_slabs4(const float* __restrict__ part, int ns, size_t stride, size_t i) {
     float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s0 = 0; s0 < ns; s0 += 16) {
-        float4 v[16];
+    for (int s0 = 0; s0 < ns; s0 += W) {
+        float4 v[W];
 #pragma unroll
-        for (int u = 0; u < 16; ++u)
+        for (int u = 0; u < W; ++u)
             v[u] = (s0 + u < ns) ? __ldcg(reinterpret_cast<const float4*>(part + (size_t)(s0 + u) * stride + i))
                                  : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int u = 0; u < 16; ++u)
+        for (int u = 0; u < W; ++u)
             if (s0 + u < ns) { x.x += v[u].x; x.y += v[u].y; x.z += v[u].z; x.w += v[u].w; }
     }
     return x;
@@ -103,7 +106,7 @@ k_finish_down4(const float* __restrict__ part, int splits, SKPlan sk, int B, int
             continue;
         }
         const int ns = finish_nslabs(sk, splits, c);
-        const float4 a4 = sum_slabs4(part, ns, n, i);
+        const float4 a4 = sum_slabs4<4>(part, ns, n, i);
         const float4 b4 = *reinterpret_cast<const float4*>(vb + c);
         const float a[4] = {a4.x, a4.y, a4.z, a4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
         float x[4], p[4], s[4], nz[4] = {0.f, 0.f, 0.f, 0.f};
@@ -157,9 +160,11 @@ k_finish_down4(const float* __restrict__ part, int splits, SKPlan sk, int B, int
     }
 }
 
+// one resident wave: 256-thread blocks of these kernels fit four to an SM (registers); a grid just above that (625
+// blocks for the 64 x 10000 finish on 132 SMs) pays a second, nearly empty wave on the critical path of the step
 inline int vec_blocks(size_t quads, int num_sms) {
     const size_t b = (quads + 255) / 256;
-    return (int)std::max<size_t>(1, std::min<size_t>(b, (size_t)num_sms * 16));
+    return (int)std::max<size_t>(1, std::min<size_t>(b, (size_t)num_sms * 4));
 }
 
 }  // namespace imdbn

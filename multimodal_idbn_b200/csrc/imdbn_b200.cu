@@ -139,11 +139,11 @@ int up_pass(imdbn_ctx* ctx, const imdbn_rbm* r, const float* v, int B, float T, 
     if (vec_ok(B, r->H, r->hb, p_out, s_out, nullptr)) {
         const size_t quads = (size_t)B * (r->H / 4);
         if (fast_math(ctx))
-            IMDBN_CUDA(ctx, launch_pdl(k_finish_up4<true>, dim3(vec_blocks(quads, ctx->num_sms)), dim3(256), 0, st,
+            IMDBN_CUDA(ctx, launch_pdl(k_finish_up4<true>, dim3(vec_blocks(quads, tc_sms(ctx))), dim3(256), 0, st,
                                        part, pl.splits, pl.sk, B, r->H, r->hb, fmaxf(1e-6f, T), 0.0f, p_out, s_out,
                                        key, draw_u, 0u));
         else
-            IMDBN_CUDA(ctx, launch_pdl(k_finish_up4<false>, dim3(vec_blocks(quads, ctx->num_sms)), dim3(256), 0, st,
+            IMDBN_CUDA(ctx, launch_pdl(k_finish_up4<false>, dim3(vec_blocks(quads, tc_sms(ctx))), dim3(256), 0, st,
                                        part, pl.splits, pl.sk, B, r->H, r->hb, fmaxf(1e-6f, T), 0.0f, p_out, s_out,
                                        key, draw_u, 0u));
     } else {
@@ -171,11 +171,11 @@ int down_pass(imdbn_ctx* ctx, const imdbn_rbm* r, const float* h, int B, float T
         const size_t quads = (size_t)B * (r->V / 4);
         ChainPost4 cp{};
         if (fast_math(ctx))
-            IMDBN_CUDA(ctx, launch_pdl(k_finish_down4<true>, dim3(vec_blocks(quads, ctx->num_sms)), dim3(256), 0, st,
+            IMDBN_CUDA(ctx, launch_pdl(k_finish_down4<true>, dim3(vec_blocks(quads, tc_sms(ctx))), dim3(256), 0, st,
                                        part, pl.splits, pl.sk, B, r->V, r->vb, fmaxf(1e-6f, T), 0.0f, p_out, lg, s_out,
                                        key, draw_u, 0u, cp));
         else
-            IMDBN_CUDA(ctx, launch_pdl(k_finish_down4<false>, dim3(vec_blocks(quads, ctx->num_sms)), dim3(256), 0, st,
+            IMDBN_CUDA(ctx, launch_pdl(k_finish_down4<false>, dim3(vec_blocks(quads, tc_sms(ctx))), dim3(256), 0, st,
                                        part, pl.splits, pl.sk, B, r->V, r->vb, fmaxf(1e-6f, T), 0.0f, p_out, lg, s_out,
                                        key, draw_u, 0u, cp));
     } else {
@@ -316,10 +316,10 @@ int run_chain_stepped(imdbn_ctx* ctx, const imdbn_rbm* r, const imdbn_chain* ch,
         int rc = gemm_up(ctx, r, v, B, pu, part, st);                                 // rbm.py:344 / 394
         if (rc) return rc;
         if (vec && fast_math(ctx))
-            IMDBN_CUDA(ctx, launch_pdl(k_finish_up4<true>, dim3(vec_blocks((size_t)B * (H / 4), ctx->num_sms)), dim3(256),
+            IMDBN_CUDA(ctx, launch_pdl(k_finish_up4<true>, dim3(vec_blocks((size_t)B * (H / 4), tc_sms(ctx))), dim3(256),
                                        0, st, part, pu.splits, pu.sk, B, H, r->hb, T, sig, h, (float*)nullptr, key, 0u, d_h));
         else if (vec)
-            IMDBN_CUDA(ctx, launch_pdl(k_finish_up4<false>, dim3(vec_blocks((size_t)B * (H / 4), ctx->num_sms)), dim3(256),
+            IMDBN_CUDA(ctx, launch_pdl(k_finish_up4<false>, dim3(vec_blocks((size_t)B * (H / 4), tc_sms(ctx))), dim3(256),
                                        0, st, part, pu.splits, pu.sk, B, H, r->hb, T, sig, h, (float*)nullptr, key, 0u, d_h));
         else
             IMDBN_CUDA(ctx, launch_pdl(k_chain_up_finish, gh, dim3(256), 0, st, part, pu.splits, pu.sk, B, H, r->hb,
@@ -354,11 +354,11 @@ int run_chain_stepped(imdbn_ctx* ctx, const imdbn_rbm* r, const imdbn_chain* ch,
         if (vec) {
             ChainPost4 cp{}; cp.enabled = 1; cp.po = po;
             if (fast_math(ctx))
-                IMDBN_CUDA(ctx, launch_pdl(k_finish_down4<true>, dim3(vec_blocks((size_t)B * (V / 4), ctx->num_sms)), dim3(256),
+                IMDBN_CUDA(ctx, launch_pdl(k_finish_down4<true>, dim3(vec_blocks((size_t)B * (V / 4), tc_sms(ctx))), dim3(256),
                                            0, st, part, pd.splits, pd.sk, B, V, r->vb, T, sig, v, lg, (float*)nullptr, key, 0u,
                                            d_v, cp));
             else
-                IMDBN_CUDA(ctx, launch_pdl(k_finish_down4<false>, dim3(vec_blocks((size_t)B * (V / 4), ctx->num_sms)), dim3(256),
+                IMDBN_CUDA(ctx, launch_pdl(k_finish_down4<false>, dim3(vec_blocks((size_t)B * (V / 4), tc_sms(ctx))), dim3(256),
                                            0, st, part, pd.splits, pd.sk, B, V, r->vb, T, sig, v, lg, (float*)nullptr, key, 0u,
                                            d_v, cp));
         } else {
@@ -647,7 +647,7 @@ int cd_core(imdbn_ctx* ctx, const imdbn_rbm* r, const float* data, int B, int k,
         // positive phase already computed together with the previous call's forward pass
         pos_h = const_cast<float*>(tail->pos_h_in);
         if (vec_ok(B, H, pos_h, h_s, nullptr, nullptr))                                               // rbm.py:203
-            IMDBN_CUDA(ctx, launch_pdl(k_bernoulli4, dim3(vec_blocks((size_t)B * (H / 4), ctx->num_sms)), dim3(256), 0, st,
+            IMDBN_CUDA(ctx, launch_pdl(k_bernoulli4, dim3(vec_blocks((size_t)B * (H / 4), tc_sms(ctx))), dim3(256), 0, st,
                                        (const float*)pos_h, B, H, h_s, key, 0u));
         else
             k_bernoulli<<<ew_blocks(nBH, ctx->num_sms), 256, 0, st>>>(pos_h, B, H, h_s, key, 0);
