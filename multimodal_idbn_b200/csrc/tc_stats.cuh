@@ -161,6 +161,15 @@ __global__ void __launch_bounds__(32 * PC_ROWS) k_pack_colstats(PackArgs a, Cols
     float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
     float sq = 0.f;
     bool nz = false;
+    // the bias and bias-momentum entries this block updates at the end: fetched now, under the row loop
+    float4 pre_m = make_float4(0.f, 0.f, 0.f, 0.f), pre_b = pre_m;
+    const bool pre_ok = ry == 0 && cs.ba.apply && col + 3 < W &&
+                        (((reinterpret_cast<uintptr_t>(is_a ? cs.ba.vbm : cs.ba.hbm) |
+                           reinterpret_cast<uintptr_t>(is_a ? cs.ba.vb : cs.ba.hb)) & 15) == 0);
+    if (pre_ok) {
+        pre_m = *reinterpret_cast<const float4*>((is_a ? cs.ba.vbm : cs.ba.hbm) + col);
+        pre_b = *reinterpret_cast<const float4*>((is_a ? cs.ba.vb : cs.ba.hb) + col);
+    }
     const int rows = a.k_chunks * ST_KC;
     constexpr int UN = 4;                          // rows in flight per thread: all their loads are issued together
     for (int r0 = ry; r0 < rows; r0 += PC_ROWS * UN) {
@@ -227,6 +236,7 @@ __global__ void __launch_bounds__(32 * PC_ROWS) k_pack_colstats(PackArgs a, Cols
             s += red_sq[q][lane];
         }
         const BiasArgs& ba = cs.ba;
+        const float pm[4] = {pre_m.x, pre_m.y, pre_m.z, pre_m.w}, pb[4] = {pre_b.x, pre_b.y, pre_b.z, pre_b.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int c = col + e;
@@ -235,17 +245,17 @@ __global__ void __launch_bounds__(32 * PC_ROWS) k_pack_colstats(PackArgs a, Cols
             if (is_a) {
                 cs.out[a.H + c] = d;
                 if (ba.apply) {                               // rbm.py:223-224 / 480-481
-                    const float m = add_rn(mul_rn(ba.vbm[c], ba.mom), mul_rn(ba.lr, d) / ba.bsz);
+                    const float m = add_rn(mul_rn(pre_ok ? pm[e] : ba.vbm[c], ba.mom), mul_rn(ba.lr, d) / ba.bsz);
                     ba.vbm[c] = m;
-                    ba.vb[c] = add_rn(ba.vb[c], m);
+                    ba.vb[c] = add_rn(pre_ok ? pb[e] : ba.vb[c], m);
                 }
             } else {
                 cs.out[c] = d; cs.out[a.H + a.V + c] = p[e];
                 if (ba.apply) {                               // rbm.py:216-220 / 478-479
-                    float m = add_rn(mul_rn(ba.hbm[c], ba.mom), mul_rn(ba.lr, d) / ba.bsz);
+                    float m = add_rn(mul_rn(pre_ok ? pm[e] : ba.hbm[c], ba.mom), mul_rn(ba.lr, d) / ba.bsz);
                     if (ba.sparsity) m = add_rn(m, mul_rn(-ba.lr, add_rn(p[e] / ba.bsz, -ba.sp_target)));
                     ba.hbm[c] = m;
-                    ba.hb[c] = add_rn(ba.hb[c], m);
+                    ba.hb[c] = add_rn(pre_ok ? pb[e] : ba.hb[c], m);
                 }
             }
         }
