@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(32 * PC_ROWS) k_pack_colstats(PackArgs a, Cols
         pre_b = *reinterpret_cast<const float4*>((is_a ? cs.ba.vb : cs.ba.hb) + col);
     }
     const int rows = a.k_chunks * ST_KC;
-    constexpr int UN = 4;                          // rows in flight per thread: all their loads are issued together
+    constexpr int UN = 8;                          // rows in flight per thread: all their loads are issued together
     for (int r0 = ry; r0 < rows; r0 += PC_ROWS * UN) {
         float4 x0[UN], x1[UN], e1[UN];
         bool valid[UN];
