@@ -137,8 +137,10 @@ struct StreamArgs {
     int w_stable;                          // W is not written by any kernel still in flight: prefetch it before the wait
     uint64_t w_policy;                     // L2 eviction priority of the W stream
     FusedFinish fin;                       // FUSE instantiation: the epilogue finishes the pass instead of storing partials;
-    int pchunks, pu_q, pu_r;               // its CTAs are persistent over (tile, batch chunk) units: unit u = tile * pchunks + chunk, CTA c
-                                           // takes pu_q (+1 for c < pu_r) consecutive units, so the epilogue of one overlaps the next one's products
+    int pchunks, punits, pband;            // its CTAs are persistent over (tile, batch chunk) units: CTA c takes the units c, c + G,
+                                           // c + 2G, ... (the epilogue of one overlaps the products of the next); unit numbers walk
+                                           // bands of `pband` tiles chunk by chunk, so the CTAs running at the same time share
+                                           // ~pband weight tiles and ~G / pband activation chunks in L2
     unsigned long long* trace;             // nullable (IMDBN_TS_TRACE): [cta][8] globaltimer stamps
 };
 
@@ -180,10 +182,20 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int cta = blockIdx.x;
     const int k_iters = a.sk.k_iters;
     // iteration range of this CTA: a stream-K share of one batch chunk (blockIdx.y), or whole (tile, chunk) units
-    const int beg = FUSE ? (cta * a.pu_q + min(cta, a.pu_r)) * k_iters : sk_beg(a.sk, cta);
-    const int end = FUSE ? ((cta + 1) * a.pu_q + min(cta + 1, a.pu_r)) * k_iters : sk_beg(a.sk, cta + 1);
-    auto tile_of = [&](int unit) { return FUSE ? unit / a.pchunks : unit; };
-    auto b0_of = [&](int unit) { return FUSE ? (unit % a.pchunks) * a.Npad : (int)blockIdx.y * a.Npad; };
+    // (FUSE: LOCAL iteration numbers, unit j of this CTA = global unit cta + j * gridDim.x)
+    const int beg = FUSE ? 0 : sk_beg(a.sk, cta);
+    const int end = FUSE ? ((a.punits - cta + (int)gridDim.x - 1) / (int)gridDim.x) * k_iters : sk_beg(a.sk, cta + 1);
+    const int m_tiles_all = (a.M_total + TS_BM - 1) / TS_BM;
+    auto unit_tc = [&](int j, int& tile, int& chunk) {      // band-major, chunk, tile inside the band
+        const int u = cta + j * (int)gridDim.x;
+        const int per_band = a.pband * a.pchunks;
+        const int band = u / per_band, r = u - band * per_band;
+        const int tb = min(a.pband, m_tiles_all - band * a.pband);       // tiles in this (possibly last, narrower) band
+        chunk = r / tb;
+        tile = band * a.pband + (r - chunk * tb);
+    };
+    auto tile_of = [&](int unit) { if (!FUSE) return unit; int t, c; unit_tc(unit, t, c); return t; };
+    auto b0_of = [&](int unit) { if (!FUSE) return (int)blockIdx.y * a.Npad; int t, c; unit_tc(unit, t, c); return c * a.Npad; };
 #ifdef IMDBN_TS_TRACE_BUILD       // nvcc -DIMDBN_TS_TRACE_BUILD: per-CTA stage stamps and counts of the waits that found their
                                   // barrier incomplete, for the launches selected by IMDBN_TS_TRACE=<first traced call>
 #define TS_MARK(i) do { if (a.trace) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.trace[(blockIdx.x + gridDim.x * blockIdx.y) * 16 + (i)] = t_; } } while (0)
@@ -685,7 +697,8 @@ static int stream_pass(imdbn_ctx* ctx, const imdbn_rbm* r, const float* act, int
         a.fin = *fin;
         const int units = ((M_total + TS_BM - 1) / TS_BM) * chunks;          // (tile, batch chunk) pairs, whole K each
         const int Gp = std::min(tc_sms(ctx), units);
-        a.pchunks = chunks; a.pu_q = units / Gp; a.pu_r = units % Gp;
+        a.pchunks = chunks; a.punits = units;
+        { static const int band_env = getenv("IMDBN_FUSE_BAND") ? atoi(getenv("IMDBN_FUSE_BAND")) : 16; a.pband = std::max(1, band_env); }
         rc = up ? launch_stream<true, false, 0, true>(ctx, tmA, tmB, tmB2, a, Gp, 1, st)
                 : launch_stream<false, false, 0, true>(ctx, tmA, tmB, tmB2, a, Gp, 1, st);
     } else if (split && a.lo_tmem == 2)
