@@ -111,9 +111,12 @@ constexpr int TS_MAX_STAGES = 8;
 constexpr int TS_NLO = 4;                  // W_lo buffers (exact mode): a ring, so the converters never wait for products
 constexpr int TS_NGRP = 2;                 // converter groups of four warps, group g takes the iterations n % 2 == g
 constexpr int TS_BAR_BYTES = 512;
-template <bool SPLIT> struct TsCfg {
+template <bool SPLIT, bool FUSE = false> struct TsCfg {
     static constexpr int BK = SPLIT ? 32 : 64;          // reduction elements per pipeline stage
-    static constexpr int THREADS = SPLIT ? 192 + TS_NGRP * 128 : 192;   // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue, 6.. converters
+    // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue, 6.. converters (exact mode) or four more epilogue warps (FUSE: the
+    // finishing epilogue of a 128 x 256 tile is ~30k clocks for one warp per lane quadrant -- as long as the products of a
+    // layer with K = 2048; two warps per quadrant split the batch columns)
+    static constexpr int THREADS = SPLIT ? 192 + TS_NGRP * 128 : (FUSE ? 320 : 192);
     static constexpr int A_BYTES = TS_BM * BK * 4;
 };
 
@@ -160,7 +163,7 @@ __device__ __forceinline__ float4 tf32_lo4(float4 x) {
 }
 
 template <bool A_MN, bool SPLIT, int LOM, bool FUSE>
-__global__ void __launch_bounds__(TsCfg<SPLIT>::THREADS, 1)
+__global__ void __launch_bounds__(TsCfg<SPLIT, FUSE>::THREADS, 1)
 k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmB2, StreamArgs a) {
     constexpr int TS_BK = TsCfg<SPLIT>::BK;
@@ -217,7 +220,7 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tma_prefetch_desc(&tmB);
         if (a.B1) tma_prefetch_desc(&tmB2);
         for (int s = 0; s < TS_MAX_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], FUSE ? 8 : 4); }
         for (int s = 0; s < TS_NLO; ++s) { mbar_init(&lo_full[s], 4); mbar_init(&lo_empty[s], 1); }
         fence_barrier_init();
     }
@@ -399,8 +402,8 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             TS_MARK(3);
             TS_MISS_FLUSH(9, 2);
         }
-    } else if (warp < 6) {
-        // ===================== epilogue: TMEM -> partial slab =====================
+    } else if (warp < (FUSE ? 10 : 6)) {
+        // ===================== epilogue: TMEM -> partial slab (FUSE: -> finished activations) =====================
         const int quad = warp & 3;                               // TMEM lane quadrant this warp may read
         int seg = 0;
         for (int cur = beg; cur < end; ++seg) {
@@ -421,7 +424,8 @@ k_tc_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const bool m_ok = m < a.M_total;
                 const float bias = m_ok ? __ldg(f.bias + m) : 0.0f;
                 const uint32_t colq = (uint32_t)(m & ~3), q = (uint32_t)lane & 3u;
-                for (int c0 = 0; c0 < a.Npad; c0 += 16) {
+                const int half = (warp - 2) >> 2, c_lo = half * (a.Npad >> 1), c_hi = c_lo + (a.Npad >> 1);    // (Npad = 256)
+                for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
                     float v[16];
                     tmem_ld16(taddr + c0, v);
                     float4 u[4];
@@ -620,7 +624,7 @@ static int launch_stream(imdbn_ctx* ctx, const CUtensorMap* tmA, const CUtensorM
         IMDBN_CUDA(ctx, cudaFuncSetAttribute(k_tc_stream<A_MN, SPLIT, LOM, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
-    IMDBN_CUDA(ctx, launch_pdl(k_tc_stream<A_MN, SPLIT, LOM, FUSE>, dim3(G, chunks), dim3(TsCfg<SPLIT>::THREADS), smem, st, *tmA, *tmB,
+    IMDBN_CUDA(ctx, launch_pdl(k_tc_stream<A_MN, SPLIT, LOM, FUSE>, dim3(G, chunks), dim3(TsCfg<SPLIT, FUSE>::THREADS), smem, st, *tmA, *tmB,
                                *tmB2, a));
     IMDBN_CHECK_LAUNCH(ctx, "k_tc_stream");
     return 0;
