@@ -262,3 +262,18 @@ def test_probe_utils_binning_split_and_probe_match_the_reference():
     assert abs(acc - float(g["probe_acc"])) < 1e-7
     cm = P.confusion_matrix(y_true, y_pred, 5)
     assert int(cm.sum()) == len(y_true) and int(cm.diag().sum()) == round(acc * len(y_true))
+
+
+def test_probe_pca_projection_matches_sklearn():
+    """probe_utils.pca_project (the device replacement of the PCA(n).fit_transform calls of idbn.py:262-283) against
+    scikit-learn on the same matrix: projections agree up to the sign of each component, variance ratios exactly."""
+    import numpy as np
+    from sklearn.decomposition import PCA
+    from multimodal_idbn_b200.probe_utils import pca_project
+    g = torch.Generator().manual_seed(3)
+    X = torch.randn(200, 24, generator=g) @ torch.diag(torch.linspace(3.0, 0.1, 24)) + 0.5
+    for k in (2, 3):
+        Z, ratio = pca_project(X, k)
+        ref = PCA(n_components=k).fit(X.numpy())
+        assert np.allclose(np.abs(Z.numpy()), np.abs(ref.transform(X.numpy())), atol=2e-4)
+        assert np.allclose(ratio.numpy(), ref.explained_variance_ratio_, atol=1e-5)
