@@ -2,13 +2,16 @@
 // by TMA straight from the fp32 master tensors (no shadow copies), warp-specialised
 // producer / MMA-issuer / epilogue roles synchronised with mbarriers.
 //
-//  k_tc_stream<A_MN>  the weight-streaming passes at small batch (HBM-bound):
+//  k_tc_stream<A_MN, SPLIT, LOM, FUSE>  the weight-streaming passes:
 //        up   (rbm.py:92)  D[h, b] = sum_v W[v,h] a[b,v]   A = W tile, MN-major (h contiguous)
 //        down (rbm.py:96)  D[v, b] = sum_h W[v,h] a[b,h]   A = W tile, K-major
 //     "swap-AB": the 128-row MMA M dimension is the OUTPUT FEATURE, the batch (<= 256) is N, so a
 //     batch of 64 uses the full datapath.  Work is stream-K partitioned (SKPlan): every CTA streams
 //     an equal, contiguous share of W exactly once; per-tile partial sums go to slabs that the finish
 //     kernels (bias / sigmoid / Philox sampling) add in a fixed order.
+//     SPLIT = exact mode (every operand as tf32 head + remainder); LOM = where the converters put the weight terms
+//     (2: tensor memory, both products read A from TMEM; 0: shared-memory ring); FUSE = large batches in the fast
+//     mode: persistent over (tile, batch chunk) units, the epilogue finishes the pass itself (no slabs, no finish kernel).
 //
 //  k_tc_stats<UPDATE> CD statistics + update (rbm.py:200,209,212-213):
 //        dS[v,h] = sum_b vp[b,v] hp[b,h] - sum_b vn[b,v] hn[b,h]   (both operands MN-major; the
